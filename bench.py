@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""bench.py -- headline benchmark of the B200 2048 environment / random-rollout path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 (N = 1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W        (N > 1, one rank per GPU)
+    python bench.py --impl reference [...]                               (CPU arm)
+
+Metric (BASELINE.json): 2048 env-steps/sec of fused random-policy rollouts.  One "step" of the
+benchmark = one pass of the hot path over one batch: every rank plays `--boards-per-gpu`
+episodes (default 2^26 = config 5's per-GPU shard; 2^29 in total at 8 GPUs) from reset to game
+over in the fused kernel, reduces them to the statistics vector and, for N > 1, all-reduces
+that vector over NCCL.  value = env-steps of all ranks / device time (max over ranks).
+
+The JSON line also carries: `e2e` (same metric through the host-buffer C-ABI entry point with
+the per-episode results copied back to pinned host memory inside the timed region), `roofline`
+(fused rollout kernel vs the integer-issue bound, as north_star prescribes for it),
+`roofline_hbm` + `kernels` (single-step kernel at 1M boards -- config 2 -- and afterstates at 8M
+boards -- config 4 -- vs the measured HBM copy peak), `cpu_baseline` (the Python port of the
+reference timed on this box's host cores) and `clocks`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+SEED = 2048
+
+
+# ---------------------------------------------------------------------- CPU arms (oracle/ is allowed here only)
+
+def cpu_python_port(episodes, cores):
+    """The reference's own algorithm and data structures (oracle/pyport.py), all host cores."""
+    from oracle import pyport
+    steps, dt = pyport.timed_rollouts(episodes, cores)
+    return steps, dt
+
+
+def cpu_c_port(episodes, threads):
+    from oracle import oracle as orc
+    orc.lib()
+    t0 = time.perf_counter()
+    _, ln = orc.rollout(episodes, SEED, 0, threads=threads)
+    dt = time.perf_counter() - t0
+    return int(ln.sum()), dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (Python port of
+    GameClient.py + rand.py + main.play; the reference itself is Python and cannot travel to
+    the GPU box), all host cores, same metric/unit/config as our arm.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    cores = host_cores()
+    per_step = args.ref_episodes_per_core * cores
+    for _ in range(args.warmup):
+        cpu_python_port(max(cores, per_step // 8), cores)
+    total_steps, total_dt = 0, 0.0
+    for _ in range(args.steps):
+        s, dt = cpu_python_port(per_step, cores)
+        total_steps += s
+        total_dt += dt
+    value = total_steps / total_dt
+    sample = "%d seeded episodes per step (seeds 0..%d), %d steps, multiprocessing.Pool(%d)" % (
+        per_step, per_step - 1, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "python int",
+        "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "what": "oracle/pyport.py: Python restatement of game/GameClient.py + control/rand.py "
+                                 "+ main.play with the reference's data structures (lists, deepcopy, random)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "episodes_per_sec": per_step * args.steps / total_dt,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "fused random-policy rollouts to game over (BASELINE configs 3 and 5): %d episodes per GPU, "
+                    "%d in total; config 3's 2^24 on one GPU is reported under rollout_config3"
+                    % (args.boards_per_gpu, args.boards_per_gpu * n_gpus),
+        "boards_per_gpu": args.boards_per_gpu, "episodes_total": args.boards_per_gpu * n_gpus,
+        "seed": SEED, "policy": "uniform random (control/rand.py)", "parallelism": "shard%d" % n_gpus,
+        "l2": "no inputs; per-episode outputs (12 B x boards_per_gpu) exceed L2; step/afterstates legs rotate "
+              "buffer sets larger than L2",
+    }
+
+
+# ---------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx),
+                "power_w_max": max(pw), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------- our arm
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def rollout_instr_per_step():
+    """SASS instructions one lane-step costs on the rollout kernel's steady-state path, taken
+    from the committed static count (profiles/rollout_sass.json, written by
+    tools/sass_stats.py --rollout-loop)."""
+    path = os.path.join(ROOT, "profiles", "rollout_sass.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["instr_per_step"]), d.get("source", path)
+    return None, "profiles/rollout_sass.json missing"
+
+
+def time_launches(torch, fn, iters):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for i in range(iters):
+        fn(i)
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / iters       # ms per launch
+
+
+def bench_step_kernel(torch, r48, hbm_peak):
+    """Config 2: 1M boards, one batched step per call, host-supplied actions already in HBM.
+    Eight rotating buffer sets (8 x 22 MB = 176 MB > 126 MB L2) so every launch reads HBM."""
+    n, sets = 1 << 20, 8
+    L = r48._native.lib()
+    # mid-game boards: 64 random steps from reset
+    env = r48.BatchedGame(n * sets, seed=SEED)
+    for _ in range(64):
+        env.step(torch.randint(0, 4, (n * sets,), device="cuda", dtype=torch.uint8))
+    boards_in = env.boards.clone()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    actions = torch.randint(0, 4, (n * sets,), device="cuda", dtype=torch.uint8, generator=g)
+    out = torch.empty_like(boards_in)
+    reward = torch.empty(n * sets, dtype=torch.int32, device="cuda")
+    done = torch.empty(n * sets, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(i):
+        o = (i % sets) * n
+        r48._native.check(L.r48_step(boards_in[o:].data_ptr(), actions[o:].data_ptr(), out[o:].data_ptr(),
+                                     reward[o:].data_ptr(), done[o:].data_ptr(), n, SEED, o, 64, 0, None, stream))
+    for i in range(16):
+        launch(i)
+    ms = time_launches(torch, launch, 400)
+    alg_bytes = 22 * n
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    res = {"workload": "config 2: 2^20 boards, one step per call, actions in HBM, 8 rotating buffer sets (176 MB > L2)",
+           "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+    # the same kernel on one 16M-board launch (352 MB): launch latency amortised
+    nbig = n * sets
+    def launch_big(i):
+        r48._native.check(L.r48_step(boards_in.data_ptr(), actions.data_ptr(), out.data_ptr(), reward.data_ptr(),
+                                     done.data_ptr(), nbig, SEED, 0, 64, 0, None, stream))
+    launch_big(0)
+    ms_big = time_launches(torch, launch_big, 20)
+    gbs_big = 22 * nbig / (ms_big * 1e-3) / 1e9
+    res["at_8M_boards"] = {"us_per_launch": ms_big * 1e3, "GBps": gbs_big, "frac": gbs_big / hbm_peak,
+                           "board_steps_per_sec": nbig / (ms_big * 1e-3)}
+    # end to end through the host-buffer entry point (pinned host memory, copies inside)
+    h_in = boards_in[:n].cpu().pin_memory()
+    h_act = actions[:n].cpu().pin_memory()
+    h_out = torch.empty(n, dtype=torch.int64).pin_memory()
+    h_rw = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_dn = torch.empty(n, dtype=torch.uint8).pin_memory()
+    def host_call():
+        r48._native.check(L.r48_step_host(h_in.data_ptr(), h_act.data_ptr(), h_out.data_ptr(), h_rw.data_ptr(),
+                                          h_dn.data_ptr(), n, SEED, 0, 64, 0, torch.cuda.current_device()))
+    for _ in range(3):
+        host_call()
+    t0 = time.perf_counter()
+    reps = 50
+    for _ in range(reps):
+        host_call()
+    dt = (time.perf_counter() - t0) / reps
+    res["e2e"] = {"value": n / dt, "unit": "board-steps/s", "h2d_bytes_per_step": 9 * n, "d2h_bytes_per_step": 13 * n,
+                  "ms_per_call": dt * 1e3}
+    return res
+
+
+def bench_afterstates_kernel(torch, r48, hbm_peak):
+    """Config 4: 8M boards, all 4 moves + game-over per board; 464 MB per launch (> L2)."""
+    n = 1 << 23
+    L = r48._native.lib()
+    env = r48.BatchedGame(n, seed=SEED)
+    for _ in range(64):
+        env.step(torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8))
+    boards = env.boards
+    out = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    reward = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+    valid = torch.empty(n, dtype=torch.uint8, device="cuda")
+    done = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(i):
+        r48._native.check(L.r48_afterstates(boards.data_ptr(), out.data_ptr(), reward.data_ptr(), valid.data_ptr(),
+                                            done.data_ptr(), n, 0, stream))
+    for i in range(3):
+        launch(i)
+    ms = time_launches(torch, launch, 20)
+    alg_bytes = 58 * n
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    return {"workload": "config 4: 2^23 boards x 4 afterstates + valid mask + done, 464 MB per launch (> L2)",
+            "us_per_launch": ms * 1e3, "boards_per_sec": n / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch N>1 with torch.distributed.run" % (args.gpus, world))
+
+    # CPU baselines first (rank 0, N = 1 only), before CUDA is initialised in this process
+    cpu_baseline = cpu_c = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        episodes = args.cpu_episodes_per_core * cores
+        steps, dt = cpu_python_port(episodes, cores)
+        cpu_baseline = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d seeded episodes (seeds 0..%d) of the same workload, multiprocessing.Pool(%d), "
+                                  "%.1f s" % (episodes, episodes - 1, cores, dt),
+                        "what": "oracle/pyport.py (Python restatement with the reference's lists/deepcopy/random)",
+                        "episodes_per_sec": episodes / dt}
+        c_eps = 60000 * cores
+        steps, dt = cpu_c_port(c_eps, cores)
+        cpu_c = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                 "sample": "%d episodes, %d pthreads, %.1f s" % (c_eps, cores, dt),
+                 "what": "oracle/r48_oracle.c (C restatement, Philox draws)"}
+
+    import torch
+    import torch.distributed as dist
+    import rein48_b200 as r48
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r48._native.check(r48._native.lib().r48_init(local_rank))
+
+    n = args.boards_per_gpu
+    base = rank * n
+    L = r48._native.lib()
+    buf = r48.RolloutBuffers(n, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    total_stats = torch.zeros(r48.STATS_WORDS, dtype=torch.int64, device=dev)
+
+    def one_step(i, events=None):
+        seed = SEED + i
+        buf.stats.zero_()
+        if events:
+            events[0].record()
+        r48._native.check(L.r48_rollout(n, seed, base, buf.final_boards.data_ptr(), buf.lengths.data_ptr(), None,
+                                        buf.workspace.data_ptr(), stream))
+        if events:
+            events[1].record()
+        r48._native.check(L.r48_episode_stats(buf.final_boards.data_ptr(), buf.lengths.data_ptr(), n,
+                                              buf.stats.data_ptr(), stream))
+        if events:
+            events[2].record()
+        r48.allreduce_stats(buf.stats)
+        if events:
+            events[3].record()
+        total_stats.add_(buf.stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(1000 + i)
+    total_stats.zero_()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        one_step(i, ev[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    k_ms = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps,
+                         sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps,
+                         sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+    elapsed_s = float(elapsed_ms.item()) * 1e-3
+    st = r48.EpisodeStats(total_stats)          # already all-reduced: whole-job counts over K steps
+    env_steps = st.steps
+    episodes = st.episodes
+    value = env_steps / elapsed_s
+
+    # ---- e2e: the public host-buffer API, per-episode results copied to pinned host memory
+    host_out = r48.RolloutResult(torch.empty(n, dtype=torch.int64).pin_memory(),
+                                 torch.empty(n, dtype=torch.int32).pin_memory(),
+                                 torch.empty(r48.STATS_WORDS, dtype=torch.int64).pin_memory())
+    r48.random_rollouts_host(n, seed=SEED + 2000, device=local_rank, board_base=base, out=host_out)
+    e2e_steps_n = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_env_steps = 0
+    for i in range(e2e_steps_n):
+        r48.random_rollouts_host(n, seed=SEED + i, device=local_rank, board_base=base, out=host_out)
+        e2e_env_steps += int(host_out.stats[r48.stats.SUM_LEN])
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_cnt = torch.tensor([e2e_env_steps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_cnt, op=dist.ReduceOp.SUM)
+    e2e = {"value": float(e2e_cnt.item()) / float(e2e_dt.item()), "unit": UNIT,
+           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (12 * n + 8 * r48.STATS_WORDS) * world,
+           "steps": e2e_steps_n, "api": "rein48_b200.random_rollouts_host -> r48_rollout_host (C ABI, host buffers)",
+           "note": "the path has no per-step host input (episodes are generated from (seed, board id)); the timed "
+                   "region includes launch, kernels, D2H of final boards + lengths + statistics and the sync"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak, peak_src = measured_peaks()
+    rollout_ms, stats_ms, reduce_ms = (float(x) for x in k_ms.tolist())
+    steps_per_launch = env_steps / args.steps / world          # per GPU
+    per_gpu_rate = steps_per_launch / (rollout_ms * 1e-3)
+    instr, instr_src = rollout_instr_per_step()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    roofline = {"bound": "issue", "kernel": "r48::rollout_kernel", "achieved": per_gpu_rate, "unit": "env-steps/s per GPU",
+                "peak": None, "frac": None, "traffic": None,
+                "ms_per_launch": rollout_ms, "share_of_step": rollout_ms / (elapsed_s * 1e3 / args.steps),
+                "algorithmic_bytes_per_launch": 12 * n,
+                "hbm_GBps_of_outputs": 12 * n / (rollout_ms * 1e-3) / 1e9}
+    if instr:
+        peak = 148 * 4 * 32 * sm_mhz * 1e6 / instr
+        roofline.update({"peak": peak, "frac": per_gpu_rate / peak, "instr_per_step": instr, "instr_source": instr_src,
+                         "peak_formula": "148 SMs x 4 schedulers x 32 lanes x sm_mhz (median under load) / "
+                                         "SASS instructions per env-step"})
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "episodes_per_sec": episodes / elapsed_s, "env_steps": env_steps, "episodes": episodes,
+        "mean_episode_length": st.mean_length, "mean_score": st.mean_score, "max_tile": st.max_tile,
+        "kernel_ms": {"rollout": rollout_ms, "episode_stats": stats_ms, "allreduce": reduce_ms},
+        "roofline": roofline,
+        "hbm_peak": {"GBps": hbm_peak, "source": peak_src},
+    }
+    if world == 1 and not args.quick:
+        buf = None
+        torch.cuda.empty_cache()
+        # config 3 exactly: 2^24 episodes on one GPU
+        n3 = 1 << 24
+        b3 = r48.RolloutBuffers(n3, dev)
+        r48.random_rollouts(n3, seed=SEED, buffers=b3)
+        ms3 = time_launches(torch, lambda i: r48.random_rollouts(n3, seed=SEED + i, buffers=b3), 3)
+        st3 = r48.EpisodeStats(b3.stats)
+        line["rollout_config3"] = {"workload": "config 3: 2^24 episodes, 1 GPU (rollout + statistics kernels)",
+                                   "ms_per_step": ms3, "env_steps_per_sec": st3.steps / (ms3 * 1e-3),
+                                   "episodes_per_sec": n3 / (ms3 * 1e-3)}
+        b3 = None
+        torch.cuda.empty_cache()
+        ks = bench_step_kernel(torch, r48, hbm_peak)
+        ka = bench_afterstates_kernel(torch, r48, hbm_peak)
+        line["kernels"] = {"step_1M": ks, "afterstates_8M": ka}
+        line["roofline_hbm"] = dict(ks["roofline"], kernel="r48::step_kernel", peak_source=peak_src)
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+        line["cpu_baseline_c"] = cpu_c
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boards-per-gpu", type=int, default=1 << 26)
+    ap.add_argument("--quick", action="store_true", help="skip the config 2/3/4 side legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-episodes-per-core", type=int, default=5000)
+    ap.add_argument("--ref-episodes-per-core", type=int, default=1500)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("note: warm-up raised to 3 (timing rule)", file=sys.stderr)
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,151 @@
+/*
+ * r48.h -- C ABI of libr48.so, the B200 (sm_100a) batched 2048 environment.
+ *
+ * The reference (nevertiree/Rein48) has no FFI: its environment is the Python class
+ * `Game` (game/GameClient.py:15-51) driven by `Rand.random_action` (control/rand.py:9-11)
+ * inside `play` (main.py:36-42).  Each entry point below replaces one of those Python
+ * call sites for a whole batch of boards; the reference line it stands for is cited.
+ * INTEGRATION.md shows the ctypes binding a Rein48 maintainer would add.
+ *
+ * Conventions
+ *   - Board = one uint64 of 16 exponent nibbles: cell (i,j) of the reference's
+ *     state_matrix[i][j] is nibble 4*i+j (nibble 0 = bits 0..3); nibble e means tile 2^e,
+ *     0 means empty.  LEFT moves toward nibble 0 of each row, UP toward row 0.
+ *   - Actions are bytes: 0 UP, 1 DOWN, 2 LEFT, 3 RIGHT (GameClient.py:140,182,206,230).
+ *   - Every pointer is a DEVICE pointer unless the function name ends in _host.  The
+ *     caller owns all buffers; device entry points allocate nothing per call (the row
+ *     tables are built once per device on first use) and only enqueue work on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).  No implicit sync.
+ *   - Return value: 0 on success, a negative R48_ERR_* otherwise; nothing throws across
+ *     the boundary.  r48_last_error() gives a thread-local message for the last failure.
+ *   - Random draws come from Philox4x32-10 keyed by (seed, global board id, tick); the
+ *     global id of element i of a batch is board_base + i.  See DESIGN.md "draw spec".
+ *   - reward_mode 0 = reference (reward is always 0, GameClient.py:138);
+ *     reward_mode 1 = merge_sum (sum of the tiles created by merges; extension).
+ */
+#ifndef R48_H
+#define R48_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R48_VERSION 100
+
+#define R48_OK             0
+#define R48_ERR_NULL      -1   /* required pointer is NULL */
+#define R48_ERR_ALIGN     -2   /* pointer not aligned to its element size */
+#define R48_ERR_ARG       -3   /* n < 0, n too large, bad reward_mode, ... */
+#define R48_ERR_CUDA      -4   /* a CUDA call failed; see r48_last_error() */
+#define R48_ERR_ACTION    -5   /* an action byte > 3 (GameClient.py:254 raises ValueError) */
+
+#define R48_UP    0
+#define R48_DOWN  1
+#define R48_LEFT  2
+#define R48_RIGHT 3
+
+/* SUM-reducible episode statistics vector (uint64 words).  One all-reduce(SUM) of this
+ * vector is the only collective of the multi-GPU rollout. */
+#define R48_STATS_EPISODES    0
+#define R48_STATS_SUM_LEN     1
+#define R48_STATS_SUM_SCORE   2
+#define R48_STATS_SUM_SCORE2  3
+#define R48_STATS_SUM_LEN2    4
+#define R48_STATS_HIST_MAXEXP 8      /* 16 bins: exponent of the largest tile */
+#define R48_STATS_HIST_LEN    24     /* 2048 bins: min(length, 2047) */
+#define R48_STATS_HIST_SCORE  2072   /* 2048 bins: min(score / 2, 2047) */
+#define R48_STATS_WORDS       4120
+
+#define R48_ROLLOUT_WORKSPACE_BYTES 256
+
+int r48_version(void);
+const char *r48_last_error(void);
+
+/* Build the per-device row tables (idempotent; other calls do it lazily). */
+int r48_init(int device);
+/* Copy the device row tables to host memory for inspection: left[65536] = result row of
+ * a LEFT move, merges[65536] = exponents of the (<= 2) merged pairs, 4 bits each. */
+int r48_debug_tables_host(uint16_t *left, uint8_t *merges, int device);
+
+/* Game.reset (GameClient.py:33-38): empty board + ONE spawned tile (tick 0). */
+int r48_reset(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, void *stream);
+
+/* Game.step (GameClient.py:40-51): move; if the board changed, spawn one tile; done =
+ * has_game_over.  `step` = number of step() calls already applied to these boards (this
+ * call is tick step+1).  in == out is allowed.  reward / done may be NULL.  `status`
+ * (optional device int32) is OR-ed with 1 if any action byte was > 3; such boards are
+ * passed through unchanged. */
+int r48_step(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
+             uint8_t *done, int64_t n, uint64_t seed, uint64_t board_base, uint32_t step,
+             int reward_mode, int32_t *status, void *stream);
+
+/* The same with the spawn draws supplied by the caller (parity mode): spawn_k[i] is what
+ * random.randint(0, n_blank-1) returned (GameClient.py:121), spawn_exp[i] is 1 for a 2,
+ * 2 for a 4 (GameClient.py:125).  Both are ignored where the move changes nothing. */
+int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *spawn_k,
+                      const uint8_t *spawn_exp, uint64_t *out, int32_t *reward, uint8_t *done,
+                      int64_t n, int reward_mode, int32_t *status, void *stream);
+
+/* Game.random_fill_grid alone (GameClient.py:102-127) with injected draws: put exponent
+ * spawn_exp[i] into the spawn_k[i]-th blank (row-major) of boards[i]; k >= n_blank leaves
+ * the board as it is (a full board is returned unchanged, GameClient.py:117-118). */
+int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,
+                       int64_t n, void *stream);
+
+/* The same with the draws made on the GPU from the Philox words of (seed, board, tick). */
+int r48_spawn(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, uint32_t tick,
+              void *stream);
+
+/* Number of blank cells per board (len(blank_grid_index_list), GameClient.py:109-114). */
+int r48_blank_counts(const uint64_t *boards, uint8_t *counts, int64_t n, void *stream);
+
+/* 1-ply afterstates: Game.update_matrix(copy, a) for a = 0..3 (GameClient.py:129-254), no
+ * spawn.  out[4*i+a], reward[4*i+a]; valid[i] bit a = move a changes the board;
+ * done[i] = Game.has_game_over (GameClient.py:65-94).  reward/valid/done may be NULL. */
+int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid,
+                    uint8_t *done, int64_t n, int reward_mode, void *stream);
+
+/* main.play with control="rand" (main.py:36-42, rand.py:9-11) for episodes
+ * board_base .. board_base+n-1, each from reset to game over, fused in one kernel.
+ * final_boards[i] / lengths[i] (steps, no-op moves included) are required outputs.
+ * If `stats` is non-NULL the R48_STATS_WORDS vector is ACCUMULATED into it (+=).
+ * `workspace` = R48_ROLLOUT_WORKSPACE_BYTES of device scratch (8-byte aligned). */
+int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                uint32_t *lengths, uint64_t *stats, void *workspace, void *stream);
+
+/* Episode statistics of finished games, accumulated into stats[R48_STATS_WORDS]. */
+int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int64_t n,
+                      uint64_t *stats, void *stream);
+
+/* np.sum(state_matrix) (main.py:48) and the largest tile's exponent, per board. */
+int r48_scores(const uint64_t *boards, uint32_t *score, uint8_t *max_exp, int64_t n,
+               void *stream);
+
+/* Board readout for the learners (np.array(state), a3c.py:195,205): out[n][4][4] tile
+ * values, or exponents when log2_planes != 0. */
+int r48_decode_f32(const uint64_t *boards, float *out, int64_t n, int log2_planes, void *stream);
+int r48_decode_i32(const uint64_t *boards, int32_t *out, int64_t n, void *stream);
+/* The inverse: tile values (0 or a power of two >= 2; anything else sets *status bit 1). */
+int r48_encode_i32(const int32_t *values, uint64_t *boards, int64_t n, int32_t *status,
+                   void *stream);
+
+/* ---- host-buffer entry points (what a CPU-side caller of the reference would bind) ----
+ * All pointers are HOST pointers (pinned memory makes the copies asynchronous); the
+ * library stages through a per-device scratch arena it owns, runs the kernels on its own
+ * stream and returns after the results are in the host buffers. */
+int r48_step_host(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
+                  uint8_t *done, int64_t n, uint64_t seed, uint64_t board_base, uint32_t step,
+                  int reward_mode, int device);
+int r48_afterstates_host(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid,
+                         uint8_t *done, int64_t n, int reward_mode, int device);
+int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                     uint32_t *lengths, uint64_t *stats, int device);
+/* Release the scratch arena and tables of every device. */
+int r48_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R48_H */

@@ -1,0 +1,22 @@
+# -*- coding: utf-8 -*-
+"""rein48_b200 -- B200-native batched 2048 environment and random-rollout path.
+
+A drop-in for the env / rollout hot path of nevertiree/Rein48 (game/GameClient.py,
+control/rand.py, main.play): hand-written sm_100a CUDA kernels behind a C ABI
+(include/r48.h, libr48.so), called from Python with zero-copy torch tensors.
+"""
+from . import _native
+from ._native import R48Error, build
+from .batched import BatchedGame, afterstates, blank_counts, decode, encode, scores, spawn_injected
+from .game import Game, action_code
+from .rand import (Rand, RolloutBuffers, RolloutResult, play, random_rollouts, random_rollouts_host,
+                   sharded_rollouts)
+from .stats import STATS_WORDS, EpisodeStats, allreduce_stats, shard_range
+
+__all__ = [
+    "BatchedGame", "Game", "Rand", "play", "random_rollouts", "random_rollouts_host",
+    "sharded_rollouts", "RolloutBuffers", "RolloutResult", "EpisodeStats", "allreduce_stats",
+    "shard_range", "afterstates", "decode", "encode", "scores", "blank_counts", "spawn_injected",
+    "action_code", "build", "R48Error", "STATS_WORDS",
+]
+__version__ = "0.1.0"

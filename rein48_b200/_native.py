@@ -1,0 +1,111 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of libr48.so (the C ABI declared in include/r48.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, this raises.
+The product path never touches oracle/ or any CPU implementation of the environment.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libr48.so")
+SRC = os.path.join(_PKG, "csrc", "r48_kernels.cu")
+DEPS = [SRC, os.path.join(_PKG, "csrc", "r48_device.cuh"), os.path.join(_ROOT, "include", "r48.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_CUDA, ERR_ACTION = 0, -1, -2, -3, -4, -5
+STATS_WORDS = 4120
+ROLLOUT_WORKSPACE_BYTES = 256
+
+# every symbol include/r48.h declares (tests check the .so exports exactly these)
+SYMBOLS = (
+    "r48_version", "r48_last_error", "r48_init", "r48_debug_tables_host", "r48_reset", "r48_step",
+    "r48_step_injected", "r48_spawn_injected", "r48_spawn", "r48_blank_counts", "r48_afterstates", "r48_rollout", "r48_episode_stats", "r48_scores",
+    "r48_decode_f32", "r48_decode_i32", "r48_encode_i32", "r48_step_host", "r48_afterstates_host",
+    "r48_rollout_host", "r48_shutdown",
+)
+
+
+class R48Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libr48 error %d: %s" % (code, message))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    """Compile libr48.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(p) for p in DEPS)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC") or "nvcc"
+    if not any(os.access(os.path.join(d, nvcc), os.X_OK) for d in os.environ.get("PATH", "").split(os.pathsep)):
+        cand = "/usr/local/cuda/bin/nvcc"
+        if os.path.exists(cand):
+            nvcc = cand
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+_u64p = C.c_void_p   # all buffers cross the ABI as raw addresses (torch data_ptr / numpy ctypes.data)
+
+
+def lib():
+    """Load libr48.so (building it first only if it is absent).  Raises if that fails."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        vp, i64, u64, u32, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int
+        L.r48_version.argtypes = []
+        L.r48_version.restype = i32
+        L.r48_last_error.argtypes = []
+        L.r48_last_error.restype = C.c_char_p
+        L.r48_init.argtypes = [i32]
+        L.r48_debug_tables_host.argtypes = [vp, vp, i32]
+        L.r48_reset.argtypes = [vp, i64, u64, u64, vp]
+        L.r48_step.argtypes = [vp, vp, vp, vp, vp, i64, u64, u64, u32, i32, vp, vp]
+        L.r48_step_injected.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp]
+        L.r48_spawn_injected.argtypes = [vp, vp, vp, i64, vp]
+        L.r48_spawn.argtypes = [vp, i64, u64, u64, u32, vp]
+        L.r48_blank_counts.argtypes = [vp, vp, i64, vp]
+        L.r48_afterstates.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
+        L.r48_rollout.argtypes = [i64, u64, u64, vp, vp, vp, vp, vp]
+        L.r48_episode_stats.argtypes = [vp, vp, i64, vp, vp]
+        L.r48_scores.argtypes = [vp, vp, vp, i64, vp]
+        L.r48_decode_f32.argtypes = [vp, vp, i64, i32, vp]
+        L.r48_decode_i32.argtypes = [vp, vp, i64, vp]
+        L.r48_encode_i32.argtypes = [vp, vp, i64, vp, vp]
+        L.r48_step_host.argtypes = [vp, vp, vp, vp, vp, i64, u64, u64, u32, i32, i32]
+        L.r48_afterstates_host.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32]
+        L.r48_rollout_host.argtypes = [i64, u64, u64, vp, vp, vp, i32]
+        L.r48_shutdown.argtypes = []
+        for name in SYMBOLS:
+            if name not in ("r48_last_error",):
+                getattr(L, name).restype = i32
+        L.r48_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().r48_last_error()
+        raise R48Error(rc, msg.decode() if msg else "")
+    return rc

@@ -1,0 +1,233 @@
+# -*- coding: utf-8 -*-
+"""BatchedGame: n 2048 boards resident on one B200, stepped by libr48's CUDA kernels.
+
+Mirrors the surface of the reference's `Game` (game/GameClient.py:15-51) for a whole batch:
+`reset()`, `step(actions)`, `state_matrix()` readout, `*_space_size` attributes.  Tensors go
+in and out zero-copy (data_ptr on the caller's CUDA stream); nothing here computes a
+transition on the host, and there is no fallback if the CUDA library is unavailable.
+"""
+import torch
+
+from . import _native
+
+REWARD_MODES = {"reference": 0, "merge_sum": 1, 0: 0, 1: 1}
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("rein48_b200 runs on CUDA devices only (got %s); there is no CPU path" % device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("rein48_b200 needs a CUDA device (B200, sm_100a); none is visible")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def as_actions(actions, device):
+    """Any integer tensor/sequence -> uint8 device tensor (values are checked on the GPU)."""
+    if not torch.is_tensor(actions):
+        actions = torch.as_tensor(actions)
+    if actions.dtype != torch.uint8:
+        # clamp so that e.g. 256 or -1 cannot wrap into a legal action byte
+        actions = actions.to(torch.int64).clamp(-1, 255).to(torch.uint8)
+    return actions.to(device, non_blocking=True).contiguous()
+
+
+class BatchedGame:
+    """n independent 4x4 games.  Boards are int64 tensors holding the uint64 bit pattern
+    (16 exponent nibbles, cell (i,j) = nibble 4*i+j).
+
+    seed / board_base key the Philox stream: board i of this batch is global board
+    board_base + i, so shards of one logical batch on different GPUs draw disjoint streams.
+    """
+
+    state_space_size = 4          # GameClient.py:21-27
+    action_space_size = 4
+    reward_space_size = 1
+    # names algorithm/ddpg/agent.py:12-14 looks for
+    state_size = 4
+    action_size = 4
+    reward_size = 1
+
+    def __init__(self, n, seed=0, device="cuda", board_base=0, reward_mode="reference"):
+        self.device = _require_cuda(device)
+        self.n = int(n)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.board_base = int(board_base)
+        self.reward_mode = REWARD_MODES[reward_mode]
+        self._lib = _native.lib()
+        with torch.cuda.device(self.device):
+            self.boards = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+            self.reward = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+            self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.steps = 0
+        self.reset()
+
+    # -- Game.reset (GameClient.py:33-38): one tile per board
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.r48_reset(self.boards.data_ptr(), self.n, self.seed,
+                                              self.board_base, _stream(self.device)))
+        self.done.zero_()
+        self.steps = 0
+        return self.boards
+
+    # -- Game.step (GameClient.py:40-51)
+    def step(self, actions):
+        """actions: integer tensor [n] in 0..3 (UP, DOWN, LEFT, RIGHT).
+        Returns (boards, reward, done) -- the same tensors every call (updated in place), as
+        the reference returns the same list object every call."""
+        a = as_actions(actions, self.device)
+        if a.numel() != self.n:
+            raise ValueError("expected %d actions, got %d" % (self.n, a.numel()))
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.r48_step(
+                self.boards.data_ptr(), a.data_ptr(), self.boards.data_ptr(), self.reward.data_ptr(),
+                self.done.data_ptr(), self.n, self.seed, self.board_base, self.steps,
+                self.reward_mode, self.status.data_ptr(), _stream(self.device)))
+        self.steps += 1
+        return self.boards, self.reward, self.done
+
+    def step_injected(self, actions, spawn_k, spawn_exp):
+        """step() with the spawn draws supplied (parity mode, see r48_step_injected)."""
+        a = as_actions(actions, self.device)
+        k = as_actions(spawn_k, self.device)
+        v = as_actions(spawn_exp, self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.r48_step_injected(
+                self.boards.data_ptr(), a.data_ptr(), k.data_ptr(), v.data_ptr(), self.boards.data_ptr(),
+                self.reward.data_ptr(), self.done.data_ptr(), self.n, self.reward_mode,
+                self.status.data_ptr(), _stream(self.device)))
+        self.steps += 1
+        return self.boards, self.reward, self.done
+
+    def check_actions(self):
+        """Synchronising check that no step() so far saw an action outside 0..3; raises the
+        ValueError the reference raises at GameClient.py:254."""
+        if int(self.status.item()) & 1:
+            self.status.zero_()
+            raise ValueError("Input action signal is wrong: actions must be 0 (UP), 1 (DOWN), 2 (LEFT), 3 (RIGHT)")
+
+    # -- 1-ply expansion (Game.update_matrix x 4 + has_game_over)
+    def afterstates(self):
+        return afterstates(self.boards, self.reward_mode)
+
+    # -- readout
+    def state_matrix(self, dtype=torch.float32, log2=False):
+        """[n, 4, 4] tile values (what np.array(state) gives the learners), or exponents."""
+        return decode(self.boards, dtype=dtype, log2=log2)
+
+    def scores(self):
+        return scores(self.boards)
+
+
+# ---------------------------------------------------------------------- functional forms
+
+def _i64(boards):
+    if boards.dtype not in (torch.int64, torch.uint64):
+        raise TypeError("boards must be int64/uint64 bit patterns")
+    if not boards.is_cuda:
+        raise RuntimeError("boards must live on a CUDA device; there is no CPU path")
+    return boards.contiguous()
+
+
+def afterstates(boards, reward_mode=0):
+    """-> (after [n,4] int64, reward [n,4] int32, valid [n] uint8 bitmask, done [n] uint8)"""
+    boards = _i64(boards)
+    n = boards.numel()
+    dev = boards.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        reward = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        done = torch.empty(n, dtype=torch.uint8, device=dev)
+        _native.check(_native.lib().r48_afterstates(
+            boards.data_ptr(), out.data_ptr(), reward.data_ptr(), valid.data_ptr(), done.data_ptr(), n,
+            REWARD_MODES[reward_mode], _stream(dev)))
+    return out, reward, valid, done
+
+
+def decode(boards, dtype=torch.float32, log2=False):
+    boards = _i64(boards)
+    n = boards.numel()
+    dev = boards.device
+    with torch.cuda.device(dev):
+        if dtype == torch.float32:
+            out = torch.empty((n, 4, 4), dtype=torch.float32, device=dev)
+            _native.check(_native.lib().r48_decode_f32(boards.data_ptr(), out.data_ptr(), n, int(bool(log2)),
+                                                      _stream(dev)))
+        elif dtype == torch.int32:
+            if log2:
+                raise ValueError("log2 planes are float32 only")
+            out = torch.empty((n, 4, 4), dtype=torch.int32, device=dev)
+            _native.check(_native.lib().r48_decode_i32(boards.data_ptr(), out.data_ptr(), n, _stream(dev)))
+        else:
+            raise TypeError("dtype must be torch.float32 or torch.int32")
+    return out
+
+
+def encode(values):
+    """[n,4,4] int32 tile values on the GPU -> packed boards; ValueError on illegal tiles."""
+    if not values.is_cuda:
+        raise RuntimeError("values must live on a CUDA device; there is no CPU path")
+    values = values.to(torch.int32).contiguous()
+    n = values.numel() // 16
+    dev = values.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n, dtype=torch.int64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _native.check(_native.lib().r48_encode_i32(values.data_ptr(), out.data_ptr(), n, status.data_ptr(),
+                                                  _stream(dev)))
+        if int(status.item()) & 2:
+            raise ValueError("tile values must be 0 or a power of two in 2..32768")
+    return out
+
+
+def scores(boards):
+    """-> (score [n] int32 = sum of tiles, max_exp [n] uint8)"""
+    boards = _i64(boards)
+    n = boards.numel()
+    dev = boards.device
+    with torch.cuda.device(dev):
+        sc = torch.empty(n, dtype=torch.int32, device=dev)
+        mx = torch.empty(n, dtype=torch.uint8, device=dev)
+        _native.check(_native.lib().r48_scores(boards.data_ptr(), sc.data_ptr(), mx.data_ptr(), n, _stream(dev)))
+    return sc, mx
+
+
+def blank_counts(boards):
+    boards = _i64(boards)
+    n = boards.numel()
+    dev = boards.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n, dtype=torch.uint8, device=dev)
+        _native.check(_native.lib().r48_blank_counts(boards.data_ptr(), out.data_ptr(), n, _stream(dev)))
+    return out
+
+
+def spawn_injected(boards, spawn_k, spawn_exp):
+    """In place: put exponent spawn_exp[i] into the spawn_k[i]-th blank of boards[i]."""
+    boards = _i64(boards)
+    dev = boards.device
+    k = as_actions(spawn_k, dev)
+    v = as_actions(spawn_exp, dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().r48_spawn_injected(boards.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                      boards.numel(), _stream(dev)))
+    return boards
+
+
+def spawn(boards, seed, board_base=0, tick=0):
+    """In place: Game.random_fill_grid with the GPU's Philox draws of (seed, board, tick)."""
+    boards = _i64(boards)
+    dev = boards.device
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().r48_spawn(boards.data_ptr(), boards.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                             int(board_base), int(tick), _stream(dev)))
+    return boards

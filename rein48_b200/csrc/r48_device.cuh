@@ -1,0 +1,268 @@
+// r48_device.cuh -- device-side building blocks of the batched 2048 environment (sm_100a).
+//
+// A board lives in two 32-bit registers: `lo` = rows 0,1 and `hi` = rows 2,3, four
+// exponent nibbles per row (cell (i,j) = nibble 4*i+j of the 64-bit word).  Everything
+// here is integer-pipe work; there is no tensor-core or floating-point math on this path.
+//
+// Reference behaviour restated by these functions (file:line in nevertiree/Rein48):
+//   move_*          Game.update_matrix           game/GameClient.py:129-254
+//   spawn_*         Game.random_fill_grid        game/GameClient.py:102-127
+//   is_stuck/...    Game.has_game_over           game/GameClient.py:65-94
+//   philox draws    random.randint/uniform       control/rand.py:11, GameClient.py:121,125
+#pragma once
+#include <stdint.h>
+
+namespace r48 {
+
+// ------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    return __byte_perm(a, b, sel);
+}
+
+// (a & m) | (b & ~m): one LOP3
+__device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b)
+{
+    return (a & m) | (b & ~m);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Salmon et al., SC'11.  The ten round keys depend only on the seed, so the host
+// precomputes them and they arrive as kernel parameters (constant bank operands).
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+
+#define R48_PHILOX_M0 0xD2511F53u
+#define R48_PHILOX_M1 0xCD9E8D57u
+#define R48_PHILOX_W0 0x9E3779B9u
+#define R48_PHILOX_W1 0xBB67AE85u
+#define R48_SPAWN4_THRESHOLD 0x1999999Au      // ceil(0.1 * 2^32): P(tile 4) = 0.1
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              const PhiloxKeys &K, uint32_t (&w)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)R48_PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)R48_PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
+// Draw spec: tick t of board `id` uses call (id.lo, id.hi, t >> 1, 0) and the
+// word pair (2*(t&1), 2*(t&1)+1) = (a, v): action = a >> 30, cell = mulhi(a << 2, n_blank),
+// value = v < THRESHOLD ? 4 : 2.
+__device__ __forceinline__ void draw_words(uint64_t id, uint32_t tick, const PhiloxKeys &K,
+                                           uint32_t &a, uint32_t &v)
+{
+    uint32_t w[4];
+    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), tick >> 1, 0u, K, w);
+    a = (tick & 1u) ? w[2] : w[0];
+    v = (tick & 1u) ? w[3] : w[1];
+}
+
+// ------------------------------------------------------------------ board symmetries
+
+// 4x4 nibble transpose: 2x2 blocks inside each word, then the off-diagonal 2x2 blocks
+// change words (two PRMTs).  10 instructions.
+__device__ __forceinline__ void transpose(uint32_t &lo, uint32_t &hi)
+{
+    uint32_t a = bsel(0x0000F0F0u, lo >> 12, bsel(0xF0F00F0Fu, lo, lo << 12));
+    uint32_t b = bsel(0x0000F0F0u, hi >> 12, bsel(0xF0F00F0Fu, hi, hi << 12));
+    lo = prmt(a, b, 0x6240);
+    hi = prmt(a, b, 0x7351);
+}
+
+// swap the two nibbles of every byte (half of a row reversal; the byte swap is folded
+// into the PRMTs that extract / re-pack rows)
+__device__ __forceinline__ uint32_t nibswap(uint32_t w)
+{
+    return bsel(0xF0F0F0F0u, w << 4, w >> 4);
+}
+
+// ------------------------------------------------------------------ the move
+// One table lookup per row: left[r] = row r after a LEFT move (toward nibble 0).
+// RIGHT = reverse rows, LEFT, reverse; UP/DOWN = transpose, LEFT/RIGHT, transpose.
+// `merges` (optional table, reward_mode 1): two 4-bit exponents of the merged pairs.
+
+template <bool WITH_REWARD>
+__device__ __forceinline__ void move(uint32_t &lo, uint32_t &hi, uint32_t action,
+                                     const uint16_t *__restrict__ left,
+                                     const uint8_t *__restrict__ merges, uint32_t &reward)
+{
+    const bool vertical = action < 2u;
+    const bool toward_high = (action & 1u) != 0u;      // DOWN or RIGHT
+    if (vertical) transpose(lo, hi);
+    if (toward_high) { lo = nibswap(lo); hi = nibswap(hi); }
+    // row -> table index; for reversed rows the PRMT also swaps the two bytes
+    const uint32_t ex0 = toward_high ? 0x4401u : 0x4410u;
+    const uint32_t ex1 = toward_high ? 0x4423u : 0x4432u;
+    const uint32_t r0 = prmt(lo, 0u, ex0), r1 = prmt(lo, 0u, ex1);
+    const uint32_t r2 = prmt(hi, 0u, ex0), r3 = prmt(hi, 0u, ex1);
+    const uint32_t o0 = left[r0], o1 = left[r1], o2 = left[r2], o3 = left[r3];
+    if (WITH_REWARD) {
+        uint32_t m = (uint32_t)merges[r0] | ((uint32_t)merges[r1] << 8) |
+                     ((uint32_t)merges[r2] << 16) | ((uint32_t)merges[r3] << 24);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) sum += (1u << ((m >> (4 * t)) & 15u)) & ~1u;
+        reward = sum << 1;                              // merging two 2^e tiles yields 2^(e+1)
+    }
+    const uint32_t pk = toward_high ? 0x4501u : 0x5410u;
+    lo = prmt(o0, o1, pk);
+    hi = prmt(o2, o3, pk);
+    if (toward_high) { lo = nibswap(lo); hi = nibswap(hi); }
+    if (vertical) transpose(lo, hi);
+}
+
+// ------------------------------------------------------------------ empties / spawn
+
+// bit 0 of every nibble = 1 where the nibble is zero
+__device__ __forceinline__ uint32_t zero_nibbles(uint32_t w)
+{
+    uint32_t t = w | (w >> 1);
+    return ~(t | (t >> 2)) & 0x11111111u;
+}
+
+// Exclusive prefix count of blanks per nibble (row-major = ascending nibble order, the
+// order of the reference's blank list, GameClient.py:109-114) and their total.
+struct Blanks {
+    uint32_t el, eh;    // blank flags
+    uint32_t ql, qh;    // q[i] = number of blanks below nibble i (0..15, never overflows)
+    uint32_t n;         // number of blanks (0..16)
+};
+
+__device__ __forceinline__ Blanks count_blanks(uint32_t lo, uint32_t hi)
+{
+    Blanks b;
+    b.el = zero_nibbles(lo);
+    b.eh = zero_nibbles(hi);
+    // (eh:el) * 0x1111111111111110 : nibble i of the product = sum of flags below i
+    uint64_t p = (uint64_t)b.el * 0x11111110u;
+    b.ql = (uint32_t)p;
+    b.qh = (uint32_t)(p >> 32) + b.el * 0x11111111u + b.eh * 0x11111110u;
+    b.n = (b.qh >> 28) + (b.eh >> 28);
+    return b;
+}
+
+// Put exponent `vexp` (1 or 2; 0 = nothing) into the k-th blank.
+__device__ __forceinline__ void place_tile(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
+                                           uint32_t vexp)
+{
+    const uint32_t kk = k * 0x11111111u;
+    const uint32_t xl = b.ql ^ kk, xh = b.qh ^ kk;       // zero nibble where q[i] == k
+    uint32_t tl = xl | (xl >> 1), th = xh | (xh >> 1);
+    const uint32_t sl = ~(tl | (tl >> 2)) & b.el;        // ... and the cell is blank: one bit
+    const uint32_t sh = ~(th | (th >> 2)) & b.eh;
+    lo += sl * vexp;
+    hi += sh * vexp;
+}
+
+// ------------------------------------------------------------------ game over
+
+// nonzero iff some nibble of y is zero (exact as an any-test)
+__device__ __forceinline__ uint32_t any_zero_nibble(uint32_t y)
+{
+    return (y - 0x11111111u) & ~y & 0x88888888u;
+}
+
+// no two equal horizontal or vertical neighbours (meaningful for a full board)
+__device__ __forceinline__ bool no_equal_neighbours(uint32_t lo, uint32_t hi)
+{
+    const uint32_t hl = (lo ^ (lo >> 4)) | 0xF000F000u;           // col 3 has no right neighbour
+    const uint32_t hh = (hi ^ (hi >> 4)) | 0xF000F000u;
+    const uint32_t vl = lo ^ prmt(lo, hi, 0x5432);                // rows 0,1 vs rows 1,2
+    const uint32_t vh = (hi ^ (hi >> 16)) | 0xFFFF0000u;          // row 2 vs row 3
+    return (any_zero_nibble(hl) | any_zero_nibble(hh) | any_zero_nibble(vl) |
+            any_zero_nibble(vh)) == 0u;
+}
+
+// Game.has_game_over: full and no equal neighbours
+__device__ __forceinline__ bool game_over(uint32_t lo, uint32_t hi)
+{
+    const bool full = (any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u;
+    return full && no_equal_neighbours(lo, hi);
+}
+
+// ------------------------------------------------------------------ readout helpers
+
+__device__ __forceinline__ uint32_t board_score(uint32_t lo, uint32_t hi)   // sum of tiles
+{
+    uint32_t s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        s += (1u << ((lo >> (4 * t)) & 15u)) & ~1u;
+        s += (1u << ((hi >> (4 * t)) & 15u)) & ~1u;
+    }
+    return s;
+}
+
+__device__ __forceinline__ uint32_t board_max_exp(uint32_t lo, uint32_t hi)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        m = max(m, (lo >> (4 * t)) & 15u);
+        m = max(m, (hi >> (4 * t)) & 15u);
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------ table staging (TMA bulk copy)
+// The 128 KB LEFT table (and the 64 KB merge table in reward mode) is copied global ->
+// shared by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) and signalled on an mbarrier,
+// so the copy overlaps the prologue (first loads, first Philox call) of each CTA.
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+}  // namespace r48

@@ -1,0 +1,1039 @@
+// r48_kernels.cu -- kernels and C ABI of libr48.so (see include/r48.h).
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//             -Xcompiler -fPIC -shared -o libr48.so r48_kernels.cu
+//
+// Kernel inventory (DESIGN.md has the roofline of each):
+//   build_tables_kernel   65536-entry LEFT-move row table + merge table, once per device
+//   reset_kernel          Game.reset                       GameClient.py:33-38
+//   step_kernel           Game.step                        GameClient.py:40-51
+//   afterstates_kernel    4 x Game.update_matrix + over    GameClient.py:129-254, 65-94
+//   rollout_kernel        main.play(control="rand")        main.py:36-42 + rand.py:9-11
+//   stats/scores/decode/encode  readout                     main.py:48, a3c.py:195,205
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+
+#include "../../include/r48.h"
+#include "r48_device.cuh"
+
+namespace r48 {
+
+constexpr int kThreads = 1024;                 // one CTA per SM (the 128 KB table fills smem)
+constexpr uint32_t kLeftBytes = 65536 * 2;
+constexpr uint32_t kMergeBytes = 65536;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------ row tables
+
+// Plain serial restatement of one row sliding LEFT (compress, merge once per pair from
+// the left, compress): runs 65536 times per device, never on the hot path.
+__device__ uint32_t slow_row_left(uint32_t r, uint32_t &merged)
+{
+    uint32_t c[4], n = 0, out = 0, o = 0, nm = 0;
+    merged = 0;
+    for (int t = 0; t < 4; t++) {
+        uint32_t e = (r >> (4 * t)) & 15u;
+        if (e) c[n++] = e;
+    }
+    for (uint32_t t = 0; t < n;) {
+        if (t + 1 < n && c[t] == c[t + 1]) {
+            uint32_t e = c[t] + 1;
+            out |= (e > 15u ? 15u : e) << (4 * o++);        // 32768+32768 saturates
+            merged |= c[t] << (4 * nm++);
+            t += 2;
+        } else {
+            out |= c[t] << (4 * o++);
+            t += 1;
+        }
+    }
+    return out;
+}
+
+__global__ void build_tables_kernel(uint16_t *left, uint8_t *merges)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < 65536u) {
+        uint32_t m;
+        left[r] = (uint16_t)slow_row_left(r, m);
+        merges[r] = (uint8_t)m;
+    }
+}
+
+// Stage the tables into shared memory with the bulk-copy engine; returns at once, the
+// caller waits on `bar` (parity 0) before its first lookup.
+template <bool REWARD>
+__device__ __forceinline__ void stage_tables(uint8_t *smem, const uint16_t *g_left,
+                                             const uint8_t *g_merges, uint64_t *bar)
+{
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, kLeftBytes + (REWARD ? kMergeBytes : 0u));
+#pragma unroll
+        for (uint32_t off = 0; off < kLeftBytes; off += 32768u)
+            bulk_g2s(smem + off, (const uint8_t *)g_left + off, 32768u, bar);
+        if (REWARD) {
+#pragma unroll
+            for (uint32_t off = 0; off < kMergeBytes; off += 32768u)
+                bulk_g2s(smem + kLeftBytes + off, g_merges + off, 32768u, bar);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ reset
+
+struct ResetParams {
+    uint64_t *boards;
+    int64_t n;
+    uint64_t board_base;
+    PhiloxKeys keys;
+};
+
+__global__ void __launch_bounds__(256) reset_kernel(ResetParams p)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t a, v;
+        draw_words(p.board_base + (uint64_t)i, 0u, p.keys, a, v);
+        uint32_t lo = 0, hi = 0;
+        Blanks b = count_blanks(lo, hi);
+        place_tile(lo, hi, b, __umulhi(a << 2, b.n), v < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+        p.boards[i] = ((uint64_t)hi << 32) | lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) spawn_injected_kernel(uint64_t *boards, const uint8_t *spawn_k,
+                                                             const uint8_t *spawn_exp, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = boards[i];
+        uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+        const Blanks bl = count_blanks(lo, hi);
+        place_tile(lo, hi, bl, spawn_k[i], spawn_exp[i] & 15u);
+        boards[i] = ((uint64_t)hi << 32) | lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) spawn_kernel(ResetParams p, uint32_t tick)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t a, v;
+        draw_words(p.board_base + (uint64_t)i, tick, p.keys, a, v);
+        const uint64_t b = p.boards[i];
+        uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+        const Blanks bl = count_blanks(lo, hi);
+        place_tile(lo, hi, bl, __umulhi(a << 2, bl.n), v < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+        p.boards[i] = ((uint64_t)hi << 32) | lo;
+    }
+}
+
+__global__ void __launch_bounds__(256) blank_counts_kernel(const uint64_t *__restrict__ boards,
+                                                           uint8_t *counts, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = boards[i];
+        counts[i] = (uint8_t)count_blanks((uint32_t)b, (uint32_t)(b >> 32)).n;
+    }
+}
+
+// ------------------------------------------------------------------ step
+
+struct StepParams {
+    const uint64_t *in;
+    const uint8_t *action;
+    const uint8_t *spawn_k;      // injected mode only
+    const uint8_t *spawn_exp;
+    uint64_t *out;
+    int32_t *reward;             // may be NULL
+    uint8_t *done;               // may be NULL
+    int32_t *status;             // may be NULL
+    int64_t n;
+    uint64_t board_base;
+    uint32_t tick;               // step + 1
+    PhiloxKeys keys;
+    const uint16_t *g_left;
+    const uint8_t *g_merges;
+};
+
+template <bool REWARD, bool INJECT>
+__device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
+                                         uint32_t vw, const uint16_t *left, const uint8_t *merges,
+                                         int32_t &reward, uint32_t &done, uint32_t &bad)
+{
+    reward = 0;
+    if (action > 3u) {                       // GameClient.py:254 raises; here: flag, pass through
+        bad = 1u;
+        done = game_over(lo, hi) ? 1u : 0u;
+        return;
+    }
+    const uint32_t olo = lo, ohi = hi;
+    uint32_t rw = 0;
+    move<REWARD>(lo, hi, action, left, merges, rw);
+    const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
+    const Blanks b = count_blanks(lo, hi);
+    uint32_t k, vexp;
+    if (INJECT) {
+        k = aw;
+        vexp = vw & 15u;
+    } else {
+        k = __umulhi(aw << 2, b.n);
+        vexp = vw < R48_SPAWN4_THRESHOLD ? 2u : 1u;
+    }
+    place_tile(lo, hi, b, k, changed ? vexp : 0u);
+    done = game_over(lo, hi) ? 1u : 0u;
+    if (REWARD) reward = (int32_t)rw;
+}
+
+// VEC: two boards per thread per trip, 128-bit board loads/stores (needs 16-byte aligned
+// in/out, 8-byte reward, 2-byte action/done); otherwise one board per thread.
+template <bool REWARD, bool INJECT, bool VEC>
+__global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const uint16_t *left = (const uint16_t *)smem;
+    const uint8_t *merges = smem + kLeftBytes;
+    stage_tables<REWARD>(smem, p.g_left, p.g_merges, &bar);
+
+    bool ready = false;
+    uint32_t bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool odd = (p.tick & 1u) != 0u;
+    if (VEC) {
+        const int64_t units = (p.n + 1) >> 1;                 // last unit may hold one board
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < units; j += stride) {
+            const bool two = 2 * j + 1 < p.n;
+            uint64_t b0, b1 = 0;
+            uint32_t a0, a1 = 0, k0 = 0, k1 = 0, v0 = 0, v1 = 0;
+            if (two) {
+                const ulonglong2 bb = ((const ulonglong2 *)p.in)[j];
+                const uchar2 aa = ((const uchar2 *)p.action)[j];
+                b0 = bb.x; b1 = bb.y; a0 = aa.x; a1 = aa.y;
+                if (INJECT) {
+                    const uchar2 kk = ((const uchar2 *)p.spawn_k)[j];
+                    const uchar2 vv = ((const uchar2 *)p.spawn_exp)[j];
+                    k0 = kk.x; k1 = kk.y; v0 = vv.x; v1 = vv.y;
+                }
+            } else {
+                b0 = p.in[2 * j];
+                a0 = p.action[2 * j];
+                if (INJECT) { k0 = p.spawn_k[2 * j]; v0 = p.spawn_exp[2 * j]; }
+            }
+            if (!INJECT) {
+                uint32_t w[4];
+                const uint64_t id0 = p.board_base + (uint64_t)(2 * j);
+                philox4x32_10((uint32_t)id0, (uint32_t)(id0 >> 32), p.tick >> 1, 0u, p.keys, w);
+                k0 = odd ? w[2] : w[0]; v0 = odd ? w[3] : w[1];
+                const uint64_t id1 = id0 + 1;
+                philox4x32_10((uint32_t)id1, (uint32_t)(id1 >> 32), p.tick >> 1, 0u, p.keys, w);
+                k1 = odd ? w[2] : w[0]; v1 = odd ? w[3] : w[1];
+            }
+            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            uint32_t lo0 = (uint32_t)b0, hi0 = (uint32_t)(b0 >> 32);
+            uint32_t lo1 = (uint32_t)b1, hi1 = (uint32_t)(b1 >> 32);
+            int32_t r0, r1 = 0;
+            uint32_t d0, d1 = 0;
+            step_one<REWARD, INJECT>(lo0, hi0, a0, k0, v0, left, merges, r0, d0, bad);
+            if (two) step_one<REWARD, INJECT>(lo1, hi1, a1, k1, v1, left, merges, r1, d1, bad);
+            if (two) {
+                ((ulonglong2 *)p.out)[j] = make_ulonglong2(((uint64_t)hi0 << 32) | lo0,
+                                                           ((uint64_t)hi1 << 32) | lo1);
+                if (p.reward) ((int2 *)p.reward)[j] = make_int2(r0, r1);
+                if (p.done) ((uchar2 *)p.done)[j] = make_uchar2((uint8_t)d0, (uint8_t)d1);
+            } else {
+                p.out[2 * j] = ((uint64_t)hi0 << 32) | lo0;
+                if (p.reward) p.reward[2 * j] = r0;
+                if (p.done) p.done[2 * j] = (uint8_t)d0;
+            }
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+            const uint64_t b0 = p.in[i];
+            const uint32_t a0 = p.action[i];
+            uint32_t k0, v0;
+            if (INJECT) {
+                k0 = p.spawn_k[i];
+                v0 = p.spawn_exp[i];
+            } else {
+                uint32_t w[4];
+                const uint64_t id0 = p.board_base + (uint64_t)i;
+                philox4x32_10((uint32_t)id0, (uint32_t)(id0 >> 32), p.tick >> 1, 0u, p.keys, w);
+                k0 = odd ? w[2] : w[0]; v0 = odd ? w[3] : w[1];
+            }
+            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            uint32_t lo0 = (uint32_t)b0, hi0 = (uint32_t)(b0 >> 32), d0;
+            int32_t r0;
+            step_one<REWARD, INJECT>(lo0, hi0, a0, k0, v0, left, merges, r0, d0, bad);
+            p.out[i] = ((uint64_t)hi0 << 32) | lo0;
+            if (p.reward) p.reward[i] = r0;
+            if (p.done) p.done[i] = (uint8_t)d0;
+        }
+    }
+    if (bad && p.status) atomicOr(p.status, 1);
+    if (!ready) mbar_wait(&bar, 0);          // never leave with the bulk copy in flight
+}
+
+// ------------------------------------------------------------------ afterstates
+
+struct AfterParams {
+    const uint64_t *in;
+    uint64_t *out;               // [n][4]
+    int32_t *reward;             // [n][4] or NULL
+    uint8_t *valid;              // [n] or NULL
+    uint8_t *done;               // [n] or NULL
+    int64_t n;
+    const uint16_t *g_left;
+    const uint8_t *g_merges;
+};
+
+template <bool REWARD>
+__global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const uint16_t *left = (const uint16_t *)smem;
+    const uint8_t *merges = smem + kLeftBytes;
+    stage_tables<REWARD>(smem, p.g_left, p.g_merges, &bar);
+
+    bool ready = false;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const uint64_t b = p.in[i];
+        if (!ready) { mbar_wait(&bar, 0); ready = true; }
+        const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+        uint64_t res[4];
+        uint32_t rw[4] = {0, 0, 0, 0};
+        uint32_t mask = 0;
+#pragma unroll
+        for (uint32_t a = 0; a < 4; a++) {
+            uint32_t l = lo, h = hi;
+            move<REWARD>(l, h, a, left, merges, rw[a]);
+            if ((l ^ lo) | (h ^ hi)) mask |= 1u << a;
+            res[a] = ((uint64_t)h << 32) | l;
+        }
+        ulonglong2 *o = (ulonglong2 *)(p.out + 4 * i);
+        o[0] = make_ulonglong2(res[0], res[1]);
+        o[1] = make_ulonglong2(res[2], res[3]);
+        if (p.reward)
+            ((int4 *)p.reward)[i] = make_int4((int)rw[0], (int)rw[1], (int)rw[2], (int)rw[3]);
+        if (p.valid) p.valid[i] = (uint8_t)mask;
+        // game over <=> no move changes a non-empty board (proof in DESIGN.md)
+        if (p.done) p.done[i] = (uint8_t)(mask == 0u && b != 0ull);
+    }
+    if (!ready) mbar_wait(&bar, 0);
+}
+
+// ------------------------------------------------------------------ fused random rollout
+
+struct RolloutParams {
+    uint64_t *final_boards;
+    uint32_t *lengths;
+    unsigned long long *counter;     // next unassigned episode
+    uint64_t n;
+    uint64_t board_base;
+    PhiloxKeys keys;
+    const uint16_t *g_left;
+};
+
+// One lane = one episode at a time, board in two registers; when its game ends the lane
+// takes the next episode index from a global counter (legal because every draw is keyed by
+// the episode's GLOBAL id and tick, not by the lane that plays it), so warps stay full
+// until the queue is empty.  One Philox call feeds two consecutive ticks.
+__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const uint16_t *left = (const uint16_t *)smem;
+    stage_tables<false>(smem, p.g_left, nullptr, &bar);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint64_t kNone = ~0ull;
+    uint32_t lo = 0, hi = 0, tick = 0, len = 0;
+    uint64_t ep = kNone;
+    bool fin = true;            // lane needs a (new) episode
+    bool live = true;           // the queue may still have work for this lane
+    bool ready = false;
+
+    for (;;) {
+        if (__any_sync(kFull, fin)) {
+            if (fin && ep != kNone) {
+                p.final_boards[ep] = ((uint64_t)hi << 32) | lo;
+                p.lengths[ep] = len;
+            }
+            const uint32_t want = __ballot_sync(kFull, fin);
+            const uint32_t leader = __ffs(want) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(want));
+            base = __shfl_sync(kFull, base, leader);
+            if (fin) {
+                const uint64_t mine = base + __popc(want & ((1u << lane) - 1u));
+                fin = false;
+                if (mine < p.n) {
+                    ep = mine; lo = 0; hi = 0; tick = 0;
+                } else {                       // queue empty: park on a dead board
+                    live = false; ep = kNone;
+                    lo = 0x12122121u; hi = 0x12122121u; tick = 2;
+                }
+            }
+            if (!__any_sync(kFull, live)) break;
+        }
+
+        uint32_t w[4];
+        const uint64_t id = p.board_base + ep;
+        philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), tick >> 1, 0u, p.keys, w);
+        if (!ready) { mbar_wait(&bar, 0); ready = true; }
+
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
+            const uint32_t olo = lo, ohi = hi;
+            uint32_t unused;
+            move<false>(lo, hi, aw >> 30, left, nullptr, unused);
+            // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
+            const bool changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
+            const Blanks b = count_blanks(lo, hi);
+            const uint32_t vexp = changed ? (vw < R48_SPAWN4_THRESHOLD ? 2u : 1u) : 0u;
+            place_tile(lo, hi, b, __umulhi(aw << 2, b.n), vexp);
+            // the board can only die on a step that filled its last blank
+            if (changed && b.n == 1u && no_equal_neighbours(lo, hi)) { fin = true; len = tick; }
+            tick++;
+        }
+    }
+    if (!ready) mbar_wait(&bar, 0);
+}
+
+// ------------------------------------------------------------------ episode statistics
+
+__global__ void __launch_bounds__(256) stats_kernel(const uint64_t *__restrict__ boards,
+                                                    const uint32_t *__restrict__ lengths, int64_t n,
+                                                    unsigned long long *stats)
+{
+    __shared__ uint32_t h_max[16], h_len[2048], h_score[2048];
+    __shared__ unsigned long long sums[5];
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) { h_len[t] = 0; h_score[t] = 0; }
+    if (threadIdx.x < 16) h_max[threadIdx.x] = 0;
+    if (threadIdx.x < 5) sums[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long s_len = 0, s_sc = 0, s_sc2 = 0, s_len2 = 0, cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = boards[i];
+        const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+        const uint32_t sc = board_score(lo, hi), mx = board_max_exp(lo, hi), ln = lengths[i];
+        atomicAdd(&h_max[mx], 1u);
+        atomicAdd(&h_len[min(ln, 2047u)], 1u);
+        atomicAdd(&h_score[min(sc >> 1, 2047u)], 1u);
+        cnt += 1; s_len += ln; s_sc += sc;
+        s_sc2 += (unsigned long long)sc * sc;
+        s_len2 += (unsigned long long)ln * ln;
+    }
+    atomicAdd(&sums[0], cnt); atomicAdd(&sums[1], s_len); atomicAdd(&sums[2], s_sc);
+    atomicAdd(&sums[3], s_sc2); atomicAdd(&sums[4], s_len2);
+    __syncthreads();
+    if (threadIdx.x < 5 && sums[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sums[threadIdx.x]);
+    if (threadIdx.x < 16 && h_max[threadIdx.x])
+        atomicAdd(&stats[R48_STATS_HIST_MAXEXP + threadIdx.x], (unsigned long long)h_max[threadIdx.x]);
+    for (int t = threadIdx.x; t < 2048; t += blockDim.x) {
+        if (h_len[t]) atomicAdd(&stats[R48_STATS_HIST_LEN + t], (unsigned long long)h_len[t]);
+        if (h_score[t]) atomicAdd(&stats[R48_STATS_HIST_SCORE + t], (unsigned long long)h_score[t]);
+    }
+}
+
+__global__ void __launch_bounds__(256) scores_kernel(const uint64_t *__restrict__ boards,
+                                                     uint32_t *score, uint8_t *max_exp, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = boards[i];
+        if (score) score[i] = board_score((uint32_t)b, (uint32_t)(b >> 32));
+        if (max_exp) max_exp[i] = (uint8_t)board_max_exp((uint32_t)b, (uint32_t)(b >> 32));
+    }
+}
+
+// ------------------------------------------------------------------ readout
+// One thread per board ROW: reads 2 bytes of the board, writes one 16-byte vector, so a
+// warp stores 512 contiguous bytes.
+
+template <typename T, bool LOG2>
+__global__ void __launch_bounds__(256) decode_kernel(const uint64_t *__restrict__ boards, T *out,
+                                                     int64_t n)
+{
+    const int64_t rows = n * 4;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = ((const uint16_t *)boards)[r];      // little endian: row r&3 of board r>>2
+        T v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint32_t e = (row >> (4 * t)) & 15u;
+            v[t] = LOG2 ? (T)e : (T)((1u << e) & ~1u);
+        }
+        if (sizeof(T) == 4) {
+            uint4 q;
+            memcpy(&q, v, 16);
+            ((uint4 *)out)[r] = q;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) encode_kernel(const int32_t *__restrict__ values,
+                                                     uint64_t *boards, int64_t n, int32_t *status)
+{
+    uint32_t bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int4 v = ((const int4 *)values)[4 * i + q];
+            const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int x = vv[t];
+                uint32_t e = 0;
+                if (x != 0) {
+                    if (x < 2 || (x & (x - 1)) || x > 32768) bad = 1;
+                    else e = 31u - __clz(x);
+                }
+                b |= (uint64_t)e << (4 * (4 * q + t));
+            }
+        }
+        boards[i] = b;
+    }
+    if (bad && status) atomicOr(status, 2);
+}
+
+}  // namespace r48
+
+using namespace r48;
+
+namespace {
+
+// ------------------------------------------------------------------ host side
+
+thread_local char g_err[256] = "";
+
+int fail(int code, const char *msg)
+{
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s", where, cudaGetErrorString(e));
+    return R48_ERR_CUDA;
+}
+
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);        \
+    } while (0)
+
+constexpr int kMaxDevices = 64;
+
+struct DeviceState {
+    bool ready = false;
+    int sms = 0;
+    uint16_t *left = nullptr;
+    uint8_t *merges = nullptr;
+    // host-API arena
+    uint8_t *arena = nullptr;
+    size_t arena_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, uint32_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int ensure_device(int dev, DeviceState **out)
+{
+    if (dev < 0 || dev >= kMaxDevices) return fail(R48_ERR_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceState &d = g_dev[dev];
+    if (!d.ready) {
+        int prev = 0;
+        CK(cudaGetDevice(&prev));
+        CK(cudaSetDevice(dev));
+        CK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaMalloc(&d.left, kLeftBytes));
+        CK(cudaMalloc(&d.merges, kMergeBytes));
+        build_tables_kernel<<<256, 256>>>(d.left, d.merges);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        CK(opt_in_smem(step_kernel<false, false, true>, kLeftBytes));
+        CK(opt_in_smem(step_kernel<false, false, false>, kLeftBytes));
+        CK(opt_in_smem(step_kernel<false, true, true>, kLeftBytes));
+        CK(opt_in_smem(step_kernel<false, true, false>, kLeftBytes));
+        CK(opt_in_smem(step_kernel<true, false, true>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(step_kernel<true, false, false>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(step_kernel<true, true, true>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(step_kernel<true, true, false>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(afterstates_kernel<false>, kLeftBytes));
+        CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(rollout_kernel, kLeftBytes));
+        CK(cudaSetDevice(prev));
+        d.ready = true;
+    }
+    *out = &d;
+    return R48_OK;
+}
+
+int current_device(DeviceState **out)
+{
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    return ensure_device(dev, out);
+}
+
+PhiloxKeys make_keys(uint64_t seed)
+{
+    PhiloxKeys k;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        k.k0[r] = k0;
+        k.k1[r] = k1;
+        k0 += R48_PHILOX_W0;
+        k1 += R48_PHILOX_W1;
+    }
+    return k;
+}
+
+inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+// grid for a grid-stride kernel of `threads`-wide blocks: enough blocks for the work,
+// capped at `per_sm` blocks per SM
+int grid_for(int64_t work_items, int threads, int sms, int per_sm)
+{
+    int64_t blocks = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int check_n(int64_t n)
+{
+    if (n < 0) return fail(R48_ERR_ARG, "n < 0");
+    if (n > ((int64_t)1 << 40)) return fail(R48_ERR_ARG, "n too large");
+    return R48_OK;
+}
+
+template <bool INJECT>
+int launch_step(const StepParams &p, int reward_mode, const DeviceState &d, cudaStream_t s)
+{
+    const bool vec = aligned(p.in, 16) && aligned(p.out, 16) && aligned(p.action, 2) &&
+                     (!p.reward || aligned(p.reward, 8)) && (!p.done || aligned(p.done, 2)) &&
+                     (!INJECT || (aligned(p.spawn_k, 2) && aligned(p.spawn_exp, 2)));
+    const int64_t units = vec ? (p.n + 1) / 2 : p.n;
+    const int grid = grid_for(units, kThreads, d.sms, 1);
+    const uint32_t smem = kLeftBytes + (reward_mode ? kMergeBytes : 0u);
+    if (reward_mode) {
+        if (vec) step_kernel<true, INJECT, true><<<grid, kThreads, smem, s>>>(p);
+        else step_kernel<true, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+    } else {
+        if (vec) step_kernel<false, INJECT, true><<<grid, kThreads, smem, s>>>(p);
+        else step_kernel<false, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+    }
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int arena_reserve(DeviceState &d, size_t bytes)
+{
+    if (!d.stream) CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    if (d.arena_bytes >= bytes) return R48_OK;
+    if (d.arena) CK(cudaFree(d.arena));
+    d.arena = nullptr;
+    d.arena_bytes = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    CK(cudaMalloc(&d.arena, want));
+    d.arena_bytes = want;
+    return R48_OK;
+}
+
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// ==================================================================== C ABI
+
+extern "C" {
+
+int r48_version(void) { return R48_VERSION; }
+
+const char *r48_last_error(void) { return g_err; }
+
+int r48_init(int device)
+{
+    DeviceState *d;
+    return ensure_device(device, &d);
+}
+
+int r48_debug_tables_host(uint16_t *left, uint8_t *merges, int device)
+{
+    if (!left || !merges) return fail(R48_ERR_NULL, "r48_debug_tables_host: NULL output");
+    DeviceState *d;
+    int rc = ensure_device(device, &d);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    CK(cudaMemcpy(left, d->left, kLeftBytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(merges, d->merges, kMergeBytes, cudaMemcpyDeviceToHost));
+    return R48_OK;
+}
+
+int r48_reset(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards) return fail(R48_ERR_NULL, "r48_reset: boards is NULL");
+    if (!aligned(boards, 8)) return fail(R48_ERR_ALIGN, "r48_reset: boards not 8-byte aligned");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    ResetParams p{boards, n, board_base, make_keys(seed)};
+    reset_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_step(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
+             uint8_t *done, int64_t n, uint64_t seed, uint64_t board_base, uint32_t step,
+             int reward_mode, int32_t *status, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_step: reward_mode must be 0 or 1");
+    if (n == 0) return R48_OK;
+    if (!in || !action || !out) return fail(R48_ERR_NULL, "r48_step: in/action/out is NULL");
+    if (!aligned(in, 8) || !aligned(out, 8) || (reward && !aligned(reward, 4)) ||
+        (status && !aligned(status, 4)))
+        return fail(R48_ERR_ALIGN, "r48_step: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    StepParams p{in, action, nullptr, nullptr, out, reward, done, status, n, board_base,
+                 step + 1u, make_keys(seed), d->left, d->merges};
+    return launch_step<false>(p, reward_mode, *d, (cudaStream_t)stream);
+}
+
+int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *spawn_k,
+                      const uint8_t *spawn_exp, uint64_t *out, int32_t *reward, uint8_t *done,
+                      int64_t n, int reward_mode, int32_t *status, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_step_injected: reward_mode must be 0 or 1");
+    if (n == 0) return R48_OK;
+    if (!in || !action || !out || !spawn_k || !spawn_exp)
+        return fail(R48_ERR_NULL, "r48_step_injected: NULL pointer");
+    if (!aligned(in, 8) || !aligned(out, 8) || (reward && !aligned(reward, 4)) ||
+        (status && !aligned(status, 4)))
+        return fail(R48_ERR_ALIGN, "r48_step_injected: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    StepParams p{in, action, spawn_k, spawn_exp, out, reward, done, status, n, 0ull,
+                 0u, make_keys(0), d->left, d->merges};
+    return launch_step<true>(p, reward_mode, *d, (cudaStream_t)stream);
+}
+
+int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,
+                       int64_t n, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards || !spawn_k || !spawn_exp) return fail(R48_ERR_NULL, "r48_spawn_injected: NULL pointer");
+    if (!aligned(boards, 8)) return fail(R48_ERR_ALIGN, "r48_spawn_injected: boards not 8-byte aligned");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    spawn_injected_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(boards, spawn_k, spawn_exp, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_spawn(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, uint32_t tick,
+              void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards) return fail(R48_ERR_NULL, "r48_spawn: boards is NULL");
+    if (!aligned(boards, 8)) return fail(R48_ERR_ALIGN, "r48_spawn: boards not 8-byte aligned");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    ResetParams p{boards, n, board_base, make_keys(seed)};
+    spawn_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(p, tick);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_blank_counts(const uint64_t *boards, uint8_t *counts, int64_t n, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards || !counts) return fail(R48_ERR_NULL, "r48_blank_counts: NULL pointer");
+    if (!aligned(boards, 8)) return fail(R48_ERR_ALIGN, "r48_blank_counts: boards not 8-byte aligned");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    blank_counts_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(boards, counts, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid,
+                    uint8_t *done, int64_t n, int reward_mode, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_afterstates: reward_mode must be 0 or 1");
+    if (n == 0) return R48_OK;
+    if (!in || !out) return fail(R48_ERR_NULL, "r48_afterstates: in/out is NULL");
+    if (!aligned(in, 8) || !aligned(out, 16) || (reward && !aligned(reward, 16)))
+        return fail(R48_ERR_ALIGN, "r48_afterstates: in needs 8-byte, out/reward 16-byte alignment");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    AfterParams p{in, out, reward, valid, done, n, d->left, d->merges};
+    const int grid = grid_for(n, kThreads, d->sms, 1);
+    if (reward_mode)
+        afterstates_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
+    else
+        afterstates_kernel<false><<<grid, kThreads, kLeftBytes, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int64_t n,
+                      uint64_t *stats, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!final_boards || !lengths || !stats) return fail(R48_ERR_NULL, "r48_episode_stats: NULL pointer");
+    if (!aligned(final_boards, 8) || !aligned(lengths, 4) || !aligned(stats, 8))
+        return fail(R48_ERR_ALIGN, "r48_episode_stats: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    stats_kernel<<<grid_for(n, 256, d->sms, 4), 256, 0, (cudaStream_t)stream>>>(
+        final_boards, lengths, n, (unsigned long long *)stats);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                uint32_t *lengths, uint64_t *stats, void *workspace, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!final_boards || !lengths || !workspace) return fail(R48_ERR_NULL, "r48_rollout: NULL pointer");
+    if (!aligned(final_boards, 8) || !aligned(lengths, 4) || !aligned(workspace, 8) ||
+        (stats && !aligned(stats, 8)))
+        return fail(R48_ERR_ALIGN, "r48_rollout: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
+    RolloutParams p{final_boards, lengths, (unsigned long long *)workspace, (uint64_t)n, board_base,
+                    make_keys(seed), d->left};
+    const int grid = grid_for(n, kThreads, d->sms, 1);
+    rollout_kernel<<<grid, kThreads, kLeftBytes, s>>>(p);
+    CK(cudaGetLastError());
+    if (stats) return r48_episode_stats(final_boards, lengths, n, stats, stream);
+    return R48_OK;
+}
+
+int r48_scores(const uint64_t *boards, uint32_t *score, uint8_t *max_exp, int64_t n, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards) return fail(R48_ERR_NULL, "r48_scores: boards is NULL");
+    if (!aligned(boards, 8) || (score && !aligned(score, 4)))
+        return fail(R48_ERR_ALIGN, "r48_scores: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    scores_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(boards, score, max_exp, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_decode_f32(const uint64_t *boards, float *out, int64_t n, int log2_planes, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards || !out) return fail(R48_ERR_NULL, "r48_decode_f32: NULL pointer");
+    if (!aligned(boards, 8) || !aligned(out, 16))
+        return fail(R48_ERR_ALIGN, "r48_decode_f32: boards needs 8-byte, out 16-byte alignment");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    const int grid = grid_for(n * 4, 256, d->sms, 8);
+    if (log2_planes) decode_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(boards, out, n);
+    else decode_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>(boards, out, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_decode_i32(const uint64_t *boards, int32_t *out, int64_t n, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards || !out) return fail(R48_ERR_NULL, "r48_decode_i32: NULL pointer");
+    if (!aligned(boards, 8) || !aligned(out, 16))
+        return fail(R48_ERR_ALIGN, "r48_decode_i32: boards needs 8-byte, out 16-byte alignment");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    decode_kernel<int32_t, false><<<grid_for(n * 4, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(boards, out, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_encode_i32(const int32_t *values, uint64_t *boards, int64_t n, int32_t *status, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!values || !boards) return fail(R48_ERR_NULL, "r48_encode_i32: NULL pointer");
+    if (!aligned(values, 16) || !aligned(boards, 8) || (status && !aligned(status, 4)))
+        return fail(R48_ERR_ALIGN, "r48_encode_i32: values needs 16-byte, boards 8-byte alignment");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    encode_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(values, boards, n, status);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+
+int r48_step_host(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
+                  uint8_t *done, int64_t n, uint64_t seed, uint64_t board_base, uint32_t step,
+                  int reward_mode, int device)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!in || !action || !out) return fail(R48_ERR_NULL, "r48_step_host: in/action/out is NULL");
+    DeviceState *d;
+    if ((rc = ensure_device(device, &d))) return rc;
+    DeviceGuard g(device);
+    const size_t nb = (size_t)n;
+    const size_t o_board = 0, o_act = up256(nb * 8), o_rew = o_act + up256(nb),
+                 o_done = o_rew + up256(nb * 4), o_status = o_done + up256(nb), total = o_status + 256;
+    if ((rc = arena_reserve(*d, total))) return rc;
+    uint64_t *d_board = (uint64_t *)(d->arena + o_board);
+    uint8_t *d_act = d->arena + o_act;
+    int32_t *d_rew = (int32_t *)(d->arena + o_rew);
+    uint8_t *d_done = d->arena + o_done;
+    int32_t *d_status = (int32_t *)(d->arena + o_status);
+    cudaStream_t s = d->stream;
+    CK(cudaMemcpyAsync(d_board, in, nb * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_act, action, nb, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_status, 0, 4, s));
+    rc = r48_step(d_board, d_act, d_board, reward ? d_rew : nullptr, done ? d_done : nullptr, n, seed,
+                  board_base, step, reward_mode, d_status, s);
+    if (rc) return rc;
+    int32_t h_status = 0;
+    CK(cudaMemcpyAsync(out, d_board, nb * 8, cudaMemcpyDeviceToHost, s));
+    if (reward) CK(cudaMemcpyAsync(reward, d_rew, nb * 4, cudaMemcpyDeviceToHost, s));
+    if (done) CK(cudaMemcpyAsync(done, d_done, nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&h_status, d_status, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_status & 1) return fail(R48_ERR_ACTION, "r48_step_host: action byte > 3");
+    return R48_OK;
+}
+
+int r48_afterstates_host(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid,
+                         uint8_t *done, int64_t n, int reward_mode, int device)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!in || !out) return fail(R48_ERR_NULL, "r48_afterstates_host: in/out is NULL");
+    DeviceState *d;
+    if ((rc = ensure_device(device, &d))) return rc;
+    DeviceGuard g(device);
+    const size_t nb = (size_t)n;
+    const size_t o_in = 0, o_out = up256(nb * 8), o_rew = o_out + up256(nb * 32),
+                 o_valid = o_rew + up256(nb * 16), o_done = o_valid + up256(nb), total = o_done + up256(nb);
+    if ((rc = arena_reserve(*d, total))) return rc;
+    uint64_t *d_in = (uint64_t *)(d->arena + o_in), *d_out = (uint64_t *)(d->arena + o_out);
+    int32_t *d_rew = (int32_t *)(d->arena + o_rew);
+    uint8_t *d_valid = d->arena + o_valid, *d_done = d->arena + o_done;
+    cudaStream_t s = d->stream;
+    CK(cudaMemcpyAsync(d_in, in, nb * 8, cudaMemcpyHostToDevice, s));
+    rc = r48_afterstates(d_in, d_out, reward ? d_rew : nullptr, valid ? d_valid : nullptr,
+                         done ? d_done : nullptr, n, reward_mode, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_out, nb * 32, cudaMemcpyDeviceToHost, s));
+    if (reward) CK(cudaMemcpyAsync(reward, d_rew, nb * 16, cudaMemcpyDeviceToHost, s));
+    if (valid) CK(cudaMemcpyAsync(valid, d_valid, nb, cudaMemcpyDeviceToHost, s));
+    if (done) CK(cudaMemcpyAsync(done, d_done, nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return R48_OK;
+}
+
+int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                     uint32_t *lengths, uint64_t *stats, int device)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    DeviceState *d;
+    if ((rc = ensure_device(device, &d))) return rc;
+    DeviceGuard g(device);
+    const size_t nb = (size_t)n;
+    const size_t o_fb = 0, o_len = up256(nb * 8), o_stats = o_len + up256(nb * 4),
+                 o_ws = o_stats + up256(R48_STATS_WORDS * 8), total = o_ws + R48_ROLLOUT_WORKSPACE_BYTES;
+    if ((rc = arena_reserve(*d, total))) return rc;
+    uint64_t *d_fb = (uint64_t *)(d->arena + o_fb);
+    uint32_t *d_len = (uint32_t *)(d->arena + o_len);
+    uint64_t *d_stats = (uint64_t *)(d->arena + o_stats);
+    cudaStream_t s = d->stream;
+    if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
+    rc = r48_rollout(n, seed, board_base, d_fb, d_len, stats ? d_stats : nullptr, d->arena + o_ws, s);
+    if (rc) return rc;
+    if (final_boards) CK(cudaMemcpyAsync(final_boards, d_fb, nb * 8, cudaMemcpyDeviceToHost, s));
+    if (lengths) CK(cudaMemcpyAsync(lengths, d_len, nb * 4, cudaMemcpyDeviceToHost, s));
+    if (stats) CK(cudaMemcpyAsync(stats, d_stats, R48_STATS_WORDS * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return R48_OK;
+}
+
+int r48_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (int dev = 0; dev < kMaxDevices; dev++) {
+        DeviceState &d = g_dev[dev];
+        if (!d.ready && !d.arena && !d.stream) continue;
+        DeviceGuard g(dev);
+        if (d.arena) cudaFree(d.arena);
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.left) cudaFree(d.left);
+        if (d.merges) cudaFree(d.merges);
+        d = DeviceState();
+    }
+    return R48_OK;
+}
+
+}  // extern "C"

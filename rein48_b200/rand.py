@@ -1,0 +1,114 @@
+# -*- coding: utf-8 -*-
+"""Random-policy driver: the reference's control/rand.py + main.play loop, batched.
+
+`Rand.random_action` keeps the reference's signature (control/rand.py:9-11).  The data path
+is `random_rollouts`: n episodes from reset to game over inside ONE fused CUDA kernel
+(r48_rollout), replacing the Python loop at main.py:36-42; multi-GPU runs give each rank a
+contiguous slice of global episode ids and all-reduce only the statistics vector.
+"""
+import random
+from collections import namedtuple
+
+import torch
+
+from . import _native
+from .batched import _require_cuda, _stream, scores
+from .stats import STATS_WORDS, EpisodeStats, allreduce_stats, shard_range
+
+ACTION_NAMES = ("UP", "DOWN", "LEFT", "RIGHT")
+
+
+class Rand:
+    """control/rand.py: a uniformly random action NAME, ignoring its arguments."""
+
+    @staticmethod
+    def random_action(*args):
+        return ACTION_NAMES[random.randint(0, 3)]
+
+
+RolloutResult = namedtuple("RolloutResult", "final_boards lengths stats")
+
+
+class RolloutBuffers:
+    """Device buffers for repeated rollouts of up to `n` episodes (allocated once)."""
+
+    def __init__(self, n, device="cuda"):
+        self.device = _require_cuda(device)
+        self.n = int(n)
+        with torch.cuda.device(self.device):
+            self.final_boards = torch.empty(self.n, dtype=torch.int64, device=self.device)
+            self.lengths = torch.empty(self.n, dtype=torch.int32, device=self.device)
+            self.stats = torch.zeros(STATS_WORDS, dtype=torch.int64, device=self.device)
+            self.workspace = torch.zeros(_native.ROLLOUT_WORKSPACE_BYTES // 8, dtype=torch.int64,
+                                         device=self.device)
+
+
+def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_stats=True):
+    """Play global episodes board_base .. board_base+n-1 to game over with the uniform random
+    policy.  Returns RolloutResult(final_boards int64[n], lengths int32[n], stats int64[4120]);
+    everything stays on the device and the call does not synchronise."""
+    if buffers is None:
+        buffers = RolloutBuffers(n, device)
+    if n > buffers.n:
+        raise ValueError("buffers hold %d episodes, asked for %d" % (buffers.n, n))
+    dev = buffers.device
+    L = _native.lib()
+    with torch.cuda.device(dev):
+        if with_stats:
+            buffers.stats.zero_()
+        _native.check(L.r48_rollout(
+            int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), buffers.final_boards.data_ptr(),
+            buffers.lengths.data_ptr(), buffers.stats.data_ptr() if with_stats else None,
+            buffers.workspace.data_ptr(), _stream(dev)))
+    return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats)
+
+
+def sharded_rollouts(n_total, seed=0, device=None, buffers=None, group=None):
+    """One rank's share of n_total episodes + the SUM all-reduce of the statistics vector.
+    Call from every rank of an initialised torch.distributed job (or standalone)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    lo, hi = shard_range(n_total, rank, world)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    res = random_rollouts(hi - lo, seed=seed, device=device, board_base=lo, buffers=buffers)
+    allreduce_stats(res.stats, group=group)
+    return res
+
+
+def random_rollouts_host(n, seed=0, device=0, board_base=0, out=None):
+    """End-to-end form over HOST buffers (r48_rollout_host): results land in pinned host
+    tensors.  Returns RolloutResult of CPU tensors."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("rein48_b200 needs a CUDA device (B200, sm_100a); none is visible")
+    if out is None:
+        out = RolloutResult(torch.empty(n, dtype=torch.int64).pin_memory(),
+                            torch.empty(n, dtype=torch.int32).pin_memory(),
+                            torch.empty(STATS_WORDS, dtype=torch.int64).pin_memory())
+    index = torch.device(device).index if not isinstance(device, int) else device
+    _native.check(_native.lib().r48_rollout_host(
+        int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), out.final_boards.data_ptr(),
+        out.lengths.data_ptr(), out.stats.data_ptr(), int(index or 0)))
+    return out
+
+
+def play(game, control="rand", show_state=False, show_result=False):
+    """main.play (main.py:11-48) for the adapter `Game`: loop the chosen policy until game
+    over and return the sum of tiles.  Only the random policy is data-parallel; "hand" is
+    the reference's interactive keyboard loop and is not provided."""
+    import numpy as np
+    if control != "rand":
+        raise NotImplementedError("only control='rand' is provided (control/hand.py is interactive)")
+    over = False
+    while not over:
+        if show_state:
+            game.print_terminal(game.state_matrix)
+        _, _, over = game.step(Rand.random_action(game.state_matrix))
+    if show_result:
+        game.print_terminal(game.state_matrix)
+    return np.sum(game.state_matrix)
+
+
+__all__ = ["Rand", "RolloutBuffers", "RolloutResult", "random_rollouts", "sharded_rollouts",
+           "random_rollouts_host", "play", "EpisodeStats", "scores"]

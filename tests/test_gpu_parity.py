@@ -1,0 +1,337 @@
+# -*- coding: utf-8 -*-
+"""GPU parity tests: the CUDA path (through libr48's C ABI) against the CPU oracle on the
+same seeded inputs and against the golden fixtures recorded from the unmodified reference.
+Integer work: the bar is bit-exact everywhere."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x2048_CAFE_F00D_0001
+BIG_BASE = (7 << 32) + 12345            # exercises the high counter word
+
+
+@pytest.fixture(scope="module")
+def r48():
+    import rein48_b200
+    rein48_b200._native.lib()
+    return rein48_b200
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def boards_to_dev(b):
+    return dev(np.asarray(b, np.uint64).view(np.int64))
+
+
+def to_u64(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def random_boards(n, seed, max_exp=11, p_zero=0.3):
+    rng = np.random.default_rng(seed)
+    e = rng.integers(1, max_exp + 1, (n, 16)).astype(np.uint64)
+    e[rng.random((n, 16)) < p_zero] = 0
+    shifts = (np.arange(16, dtype=np.uint64) * np.uint64(4))
+    return (e << shifts).sum(axis=1).astype(np.uint64)
+
+
+# ------------------------------------------------------------------ row tables
+
+def test_row_tables_exhaustive(r48, orc, golden):
+    """The device-built LEFT table against the oracle for all 65536 rows, and against the
+    reference's recorded outputs (exponent 16 = 65536 clamps to 15, the documented edge)."""
+    left = np.zeros(65536, np.uint16)
+    merges = np.zeros(65536, np.uint8)
+    L = r48._native.lib()
+    r48._native.check(L.r48_debug_tables_host(left.ctypes.data, merges.ctypes.data, 0))
+    ref = np.minimum(golden("rows_ref.npz")["out_exp"][2], 15).astype(np.uint32)   # action 2 = LEFT
+    want = ref[:, 0] | (ref[:, 1] << 4) | (ref[:, 2] << 8) | (ref[:, 3] << 12)
+    assert (left == want).all()
+    for r in range(0, 65536, 3):
+        out, _, gained = orc.move(r, 2)
+        assert left[r] == out
+        m = int(merges[r])
+        assert gained == sum((2 << e) for e in (m & 15, m >> 4) if e)
+
+
+# ------------------------------------------------------------------ afterstates (update_matrix x 4)
+
+def test_afterstates_golden_boards(r48, golden):
+    g = golden("boards_ref.npz")
+    after, reward, valid, done = r48.afterstates(boards_to_dev(g["boards"]))
+    assert (to_u64(after) == g["after"]).all()
+    changed = (valid.cpu().numpy()[:, None] >> np.arange(4)) & 1
+    assert (changed == g["changed"]).all()
+    assert (done.cpu().numpy() == g["over"]).all()
+    assert (reward == 0).all()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_afterstates_vs_oracle(r48, orc, mode):
+    b = np.concatenate([random_boards(150000, 1), random_boards(50000, 2, max_exp=15, p_zero=0.1),
+                        random_boards(50000, 3, max_exp=3, p_zero=0.0), np.zeros(3, np.uint64)])
+    after, reward, valid, done = r48.afterstates(boards_to_dev(b), reward_mode=mode)
+    o_after, o_reward, o_valid, o_done = orc.afterstates_batch(b, reward_mode=mode)
+    assert (to_u64(after) == o_after).all()
+    assert (reward.cpu().numpy() == o_reward).all()
+    assert (valid.cpu().numpy() == o_valid).all()
+    assert (done.cpu().numpy() == o_done).all()
+
+
+# ------------------------------------------------------------------ step, draws injected (the reference's own games)
+
+def test_step_injected_reference_episodes(r48, golden):
+    g = golden("episodes_ref.npz")
+    n = g["before"].size
+    env = r48.BatchedGame(n)
+    env.boards.copy_(boards_to_dev(g["before"]))
+    boards, reward, done = env.step_injected(dev(g["action"]), dev(g["k"]), dev(g["vexp"]))
+    assert (to_u64(boards) == g["after"]).all()
+    assert (done.cpu().numpy() == g["done"]).all()
+    assert (reward == 0).all()
+
+
+def test_step_injected_vs_oracle_ragged(r48, orc):
+    """odd sizes and misaligned views take the scalar kernel; both must agree with the oracle"""
+    rng = np.random.default_rng(11)
+    for n, off in ((1, 0), (2, 0), (3, 1), (1025, 0), (4097, 1), (65537, 3)):
+        b = random_boards(n + off, 100 + n)
+        a = rng.integers(0, 4, n + off).astype(np.uint8)
+        k = rng.integers(0, 16, n + off).astype(np.uint8)
+        v = rng.integers(1, 3, n + off).astype(np.uint8)
+        # k must be < n_blank of the moved board for the oracle; reduce modulo that count
+        moved, _, _, _ = orc.afterstates_batch(b)
+        blanks = np.array([sum(((int(m) >> (4 * p)) & 15) == 0 for p in range(16))
+                           for m in moved[np.arange(n + off), a]])
+        k = np.where(blanks > 0, k % np.maximum(blanks, 1), 0).astype(np.uint8)
+        L = r48._native.lib()
+        d_in, d_a, d_k, d_v = boards_to_dev(b), dev(a), dev(k), dev(v)
+        d_out = torch.zeros(n + off, dtype=torch.int64, device="cuda")
+        d_r = torch.zeros(n + off, dtype=torch.int32, device="cuda")
+        d_d = torch.zeros(n + off, dtype=torch.uint8, device="cuda")
+        r48._native.check(L.r48_step_injected(
+            d_in[off:].data_ptr(), d_a[off:].data_ptr(), d_k[off:].data_ptr(), d_v[off:].data_ptr(),
+            d_out[off:].data_ptr(), d_r[off:].data_ptr(), d_d[off:].data_ptr(), n, 1, None, None))
+        o_out, o_r, o_d = orc.step_injected_batch(b[off:], a[off:], k[off:], v[off:], reward_mode=1)
+        assert (to_u64(d_out)[off:] == o_out).all()
+        assert (d_r.cpu().numpy()[off:] == o_r).all()
+        assert (d_d.cpu().numpy()[off:] == o_d).all()
+
+
+# ------------------------------------------------------------------ step / reset with Philox draws
+
+def test_reset_vs_oracle(r48, orc):
+    n = 100003
+    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE)
+    assert (to_u64(env.boards) == orc.reset_batch(n, SEED, BIG_BASE)).all()
+
+
+@pytest.mark.parametrize("step", [0, 1, 62, 63, 1000001])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_step_vs_oracle(r48, orc, step, mode):
+    n = 120001
+    b = random_boards(n, 7 + step % 5)
+    a = np.random.default_rng(step).integers(0, 4, n).astype(np.uint8)
+    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE, reward_mode=mode)
+    env.boards.copy_(boards_to_dev(b))
+    env.steps = step
+    boards, reward, done = env.step(dev(a))
+    o_b, o_r, o_d = orc.step_batch(b, a, SEED, BIG_BASE, step, reward_mode=mode)
+    assert (to_u64(boards) == o_b).all()
+    assert (reward.cpu().numpy() == o_r).all()
+    assert (done.cpu().numpy() == o_d).all()
+    env.check_actions()
+
+
+def test_step_bad_action_flag(r48):
+    env = r48.BatchedGame(1000, seed=1)
+    before = env.boards.clone()
+    a = torch.full((1000,), 2, dtype=torch.int64, device="cuda")
+    a[17] = 4
+    a[500] = -1
+    a[501] = 256          # must not wrap into action 0
+    env.step(a)
+    with pytest.raises(ValueError):
+        env.check_actions()
+    for i in (17, 500, 501):
+        assert env.boards[i] == before[i]
+
+
+def test_spawn_vs_oracle(r48, orc):
+    """spawn-only op == the oracle's spawn of the same tick (through orc_step on a board that
+    certainly changes is awkward, so compare against the draw spec directly)."""
+    n = 20000
+    b = random_boards(n, 31, p_zero=0.5)
+    d = boards_to_dev(b)
+    from rein48_b200.batched import spawn
+    spawn(d, SEED, BIG_BASE, tick=5)
+    got = to_u64(d)
+    for i in range(0, n, 37):
+        a, v = orc.draw(SEED, BIG_BASE + i, 5)
+        m = orc.decode(b[i])
+        nb = int((m == 0).sum())
+        if nb:
+            k = (((a << 2) & 0xFFFFFFFF) * nb) >> 32
+            m, _ = orc.random_fill_grid(m, k, 4 if v < 0x1999999A else 2)
+        assert orc.encode(m) == int(got[i])
+
+
+# ------------------------------------------------------------------ fused rollout
+
+def test_rollout_bit_exact_vs_oracle(r48, orc):
+    n = 30000
+    res = r48.random_rollouts(n, seed=SEED, board_base=BIG_BASE)
+    fb, ln = orc.rollout(n, SEED, BIG_BASE, threads=8)
+    assert (to_u64(res.final_boards) == fb).all()
+    assert (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
+    assert (res.stats.cpu().numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
+
+
+def test_rollout_equals_repeated_step(r48):
+    """the fused kernel is the step kernel applied tick by tick with the Philox actions"""
+    n = 4096
+    seed, base = 99, 1 << 33
+    res = r48.random_rollouts(n, seed=seed, board_base=base)
+    env = r48.BatchedGame(n, seed=seed, board_base=base)
+    alive = torch.ones(n, dtype=torch.bool, device="cuda")
+    length = torch.zeros(n, dtype=torch.int32, device="cuda")
+    frozen = env.boards.clone()
+    from oracle import oracle as orc
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(base)
+    while bool(alive.any()):
+        acts = np.array([orc.draw(seed, int(i), env.steps + 1)[0] >> 30 for i in ids], np.uint8)
+        boards, _, done = env.step(dev(acts))
+        frozen = torch.where(alive, boards, frozen)
+        env.boards.copy_(frozen)
+        length += alive.to(torch.int32)
+        alive &= done == 0
+    assert (frozen == res.final_boards).all()
+    assert (length == res.lengths).all()
+
+
+def test_rollout_shards_reduce_to_whole(r48):
+    """stats of [0,n) == stats of [0,n/2) + stats of [n/2,n): what makes the all-reduce exact"""
+    n = 50000
+    whole = r48.random_rollouts(n, seed=5).stats.clone()
+    a = r48.random_rollouts(n // 2, seed=5, board_base=0).stats.clone()
+    b = r48.random_rollouts(n - n // 2, seed=5, board_base=n // 2).stats.clone()
+    assert (a + b == whole).all()
+
+
+def test_rollout_host_entry(r48, orc):
+    n = 5000
+    out = r48.random_rollouts_host(n, seed=3, board_base=17)
+    fb, ln = orc.rollout(n, 3, 17, threads=4)
+    assert (out.final_boards.numpy().view(np.uint64) == fb).all()
+    assert (out.lengths.numpy().view(np.uint32) == ln).all()
+    assert (out.stats.numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
+
+
+def test_step_host_entry(r48, orc):
+    n = 70001
+    b = random_boards(n, 77)
+    a = np.random.default_rng(3).integers(0, 4, n).astype(np.uint8)
+    out = np.zeros(n, np.uint64)
+    rw = np.zeros(n, np.int32)
+    dn = np.zeros(n, np.uint8)
+    L = r48._native.lib()
+    r48._native.check(L.r48_step_host(b.ctypes.data, a.ctypes.data, out.ctypes.data, rw.ctypes.data,
+                                      dn.ctypes.data, n, SEED, 5, 9, 1, 0))
+    o_b, o_r, o_d = orc.step_batch(b, a, SEED, 5, 9, reward_mode=1)
+    assert (out == o_b).all() and (rw == o_r).all() and (dn == o_d).all()
+    a[5] = 9
+    assert L.r48_step_host(b.ctypes.data, a.ctypes.data, out.ctypes.data, None, None, n, SEED, 5, 9, 0, 0) == -5
+
+
+def test_afterstates_host_entry(r48, orc):
+    n = 33333
+    b = random_boards(n, 78)
+    out = np.zeros((n, 4), np.uint64)
+    rw = np.zeros((n, 4), np.int32)
+    va = np.zeros(n, np.uint8)
+    dn = np.zeros(n, np.uint8)
+    L = r48._native.lib()
+    r48._native.check(L.r48_afterstates_host(b.ctypes.data, out.ctypes.data, rw.ctypes.data, va.ctypes.data,
+                                             dn.ctypes.data, n, 1, 0))
+    o = orc.afterstates_batch(b, reward_mode=1)
+    assert (out == o[0]).all() and (rw == o[1]).all() and (va == o[2]).all() and (dn == o[3]).all()
+
+
+# ------------------------------------------------------------------ readout
+
+def test_decode_encode_scores(r48, orc):
+    b = np.concatenate([random_boards(50001, 5, max_exp=15), np.zeros(1, np.uint64)])
+    d = boards_to_dev(b)
+    assert (r48.decode(d).cpu().numpy() == orc.decode_batch(b, "float32")).all()
+    assert (r48.decode(d, log2=True).cpu().numpy() == orc.decode_batch(b, "float32", True)).all()
+    vals = r48.decode(d, dtype=torch.int32)
+    assert (vals.cpu().numpy() == orc.decode_batch(b, "int32")).all()
+    assert (r48.encode(vals) == d).all()
+    sc, mx = r48.scores(d)
+    assert (sc.cpu().numpy()[:2000] == orc.scores(b[:2000])).all()
+    assert (mx.cpu().numpy()[:2000] == orc.max_exps(b[:2000])).all()
+    nb = r48.blank_counts(d).cpu().numpy()
+    assert (nb == (orc.decode_batch(b, "int32") == 0).reshape(-1, 16).sum(1)).all()
+    bad = vals.clone()
+    bad[3, 1, 1] = 3
+    with pytest.raises(ValueError):
+        r48.encode(bad)
+
+
+# ------------------------------------------------------------------ Game adapter: the reference's games, replayed
+
+def test_game_adapter_replays_reference_seeds(r48, golden):
+    """random.seed(s); Game(); play(game, 'rand') must reproduce the reference's episode for
+    seed s (steps, score, max tile) -- fingerprints recorded from the unmodified reference."""
+    import random
+    fp = golden("episodes_ref.npz")["fingerprint"]
+    for s in (0, 1, 2):
+        random.seed(s)
+        g = r48.Game()
+        steps = 0
+        over = False
+        while not over:
+            state, reward, over = g.step(r48.Rand.random_action(g.state_matrix))
+            assert reward == 0
+            steps += 1
+        assert state is g.state_matrix                    # same list object, as in the reference
+        assert (steps, int(np.sum(state)), int(np.max(state))) == tuple(fp[s])
+
+
+def test_game_adapter_surface(r48, golden):
+    import random
+    g = r48.Game(2)                                       # sizes < 4 clamp to 4 (GameClient.py:24-27)
+    assert (g.state_space_size, g.action_space_size, g.reward_space_size) == (4, 4, 1)
+    assert (g.state_size, g.action_size, g.reward_size) == (4, 4, 1)
+    assert sum(v != 0 for row in g.state_matrix for v in row) == 1      # reset spawns ONE tile
+    with pytest.raises(ValueError):
+        g.step("X")
+    with pytest.raises(NotImplementedError):
+        r48.Game(5)
+    tv = golden("testvectors_ref.npz")
+    # GameClientTest.py vectors scaled by 2 (tile "1" is not a power of two >= 2)
+    for a, name in enumerate(("U", "D", "L", "R")):
+        for cells, want in zip(tv["lines"], tv["moved"][a]):
+            m = [[0] * 4 for _ in range(4)]
+            for t, c in enumerate(cells):
+                if a < 2:
+                    m[t][0] = int(2 * c)
+                else:
+                    m[0][t] = int(2 * c)
+            out, reward, _ = r48.Game.update_matrix(m, name)
+            line = [out[t][0] for t in range(4)] if a < 2 else out[0]
+            assert line == [int(2 * w) for w in want] and reward == 0
+    for b, want in zip(tv["over_boards"], tv["over"]):
+        assert r48.Game.has_game_over(b.tolist()) == bool(want)
+    assert r48.Game.has_table_filled([[2] * 4] * 4) and not r48.Game.has_table_filled([[2, 0, 2, 2]] + [[2] * 4] * 3)
+    full = [[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]]
+    assert r48.Game.random_fill_grid([r[:] for r in full]) == full      # GameClientTest.py:43-44
+    gp = r48.Game(rng="philox", seed=5, board_id=3)
+    assert r48.play(gp, "rand") == np.sum(gp.state_matrix)
