@@ -46,6 +46,8 @@ def test_spawn_chi_square(r48):
         for p in cells[nb:]:
             board |= int(rng.integers(1, 12)) << (4 * int(p))
         blanks = np.sort(cells[:nb])
+        if board >= 1 << 63:
+            board -= 1 << 64                                   # int64 bit pattern
         b = torch.full((per,), board, dtype=torch.int64, device="cuda")
         spawn(b, seed=424242 + nb, board_base=nb * 10_000_000, tick=nb)
         diff = (b ^ board)
