@@ -234,6 +234,20 @@ def bench_step_kernel(torch, r48, hbm_peak):
     gbs_big = 22 * nbig / (ms_big * 1e-3) / 1e9
     res["at_8M_boards"] = {"us_per_launch": ms_big * 1e3, "GBps": gbs_big, "frac": gbs_big / hbm_peak,
                            "board_steps_per_sec": nbig / (ms_big * 1e-3)}
+    # size sweep (1M boards is launch/staging-latency sized); windows rotate through the 8M buffer
+    sweep = {}
+    for lg in (16, 18, 19, 20, 21, 22, 23):
+        m = 1 << lg
+        wins = max(1, nbig // m)
+        def launch_m(i, m=m, wins=wins):
+            o = (i % wins) * m
+            r48._native.check(L.r48_step(boards_in[o:].data_ptr(), actions[o:].data_ptr(), out[o:].data_ptr(),
+                                         reward[o:].data_ptr(), done[o:].data_ptr(), m, SEED, o, 64, 0, None, stream))
+        for i in range(4):
+            launch_m(i)
+        t = time_launches(torch, launch_m, 100 if lg <= 21 else 20)
+        sweep["2^%d" % lg] = {"us": t * 1e3, "GBps": 22 * m / (t * 1e-3) / 1e9}
+    res["size_sweep"] = sweep
     # end to end through the host-buffer entry point (pinned host memory, copies inside)
     h_in = boards_in[:n].cpu().pin_memory()
     h_act = actions[:n].cpu().pin_memory()

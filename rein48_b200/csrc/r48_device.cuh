@@ -21,10 +21,13 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return __byte_perm(a, b, sel);
 }
 
-// (a & m) | (b & ~m): one LOP3
+// (a & m) | (b & ~m) as exactly one LOP3 (ptxas otherwise re-derives it from known-zero
+// bits of the shifted operands and spends an extra instruction per select)
 __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b)
 {
-    return (a & m) | (b & ~m);
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
+    return d;
 }
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -89,13 +92,13 @@ __device__ __forceinline__ uint32_t nibswap(uint32_t w)
     return bsel(0xF0F0F0F0u, w << 4, w >> 4);
 }
 
-// ------------------------------------------------------------------ the move
-// One table lookup per row: left[r] = row r after a LEFT move (toward nibble 0).
-// RIGHT = reverse rows, LEFT, reverse; UP/DOWN = transpose, LEFT/RIGHT, transpose.
-// `merges` (optional table, reward_mode 1): two 4-bit exponents of the merged pairs.
+// ------------------------------------------------------------------ the move, 16-bit tables
+// (reward_mode 1 kernels).  One lookup per row: left[r] = row r after a LEFT move (toward
+// nibble 0).  RIGHT = reverse rows, LEFT, reverse; UP/DOWN = transpose, LEFT/RIGHT,
+// transpose.  `merges`: two 4-bit exponents of the merged pairs of the row.
 
 template <bool WITH_REWARD>
-__device__ __forceinline__ void move(uint32_t &lo, uint32_t &hi, uint32_t action,
+__device__ __forceinline__ void move_l16(uint32_t &lo, uint32_t &hi, uint32_t action,
                                      const uint16_t *__restrict__ left,
                                      const uint8_t *__restrict__ merges, uint32_t &reward)
 {
@@ -124,19 +127,105 @@ __device__ __forceinline__ void move(uint32_t &lo, uint32_t &hi, uint32_t action
     if (vertical) transpose(lo, hi);
 }
 
+// ------------------------------------------------------------------ the move, LR table
+// (reward_mode 0 kernels: step, afterstates, rollout).  lr[r] = LEFT result of row r in the
+// low half, RIGHT result in the high half, for r < kLrRows (rows whose last cell is below
+// 2^14 -- 224 KB, what fits beside nothing else in one SM's shared memory).  One lookup per
+// row serves both directions, so there is no row reversal; the PRMT that re-packs two rows
+// picks the half.  Rows outside the table (a 16384 or 32768 tile in the last cell) take a
+// serial path; random play never gets there, strong players occasionally do.
+
+constexpr uint32_t kLrRows = 0xE000u;               // 57344 entries x 4 B = 229376 B
+
+__device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
+{
+    // compress / merge-once / compress, toward nibble 0 or toward nibble 3
+    uint32_t c[4], n = 0, out = 0, o = 0;
+    for (int t = 0; t < 4; t++) {
+        const uint32_t e = (r >> (4 * (toward_high ? 3 - t : t))) & 15u;
+        if (e) c[n++] = e;
+    }
+    for (uint32_t t = 0; t < n;) {
+        uint32_t e = c[t];
+        if (t + 1 < n && c[t] == c[t + 1]) { e = e + 1 > 15u ? 15u : e + 1; t += 2; }
+        else t += 1;
+        out |= e << (4 * (toward_high ? 3 - o : o));
+        o++;
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t lr_lookup(const uint32_t *lr, uint32_t r, bool toward_high)
+{
+    if (r < kLrRows) return lr[r];
+    const uint32_t o = slow_row(r, toward_high);
+    return o | (o << 16);
+}
+
+__device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t action,
+                                        const uint32_t *__restrict__ lr)
+{
+    const bool vertical = action < 2u;
+    const bool toward_high = (action & 1u) != 0u;      // DOWN or RIGHT
+    if (vertical) transpose(lo, hi);
+    const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
+    uint32_t o0, o1, o2, o3;
+    if (__builtin_expect((r0 | r1 | r2 | r3) < kLrRows, 1)) {   // OR >= any row: conservative
+        o0 = lr[r0]; o1 = lr[r1]; o2 = lr[r2]; o3 = lr[r3];
+    } else {
+        o0 = lr_lookup(lr, r0, toward_high); o1 = lr_lookup(lr, r1, toward_high);
+        o2 = lr_lookup(lr, r2, toward_high); o3 = lr_lookup(lr, r3, toward_high);
+    }
+    const uint32_t pk = toward_high ? 0x7632u : 0x5410u;
+    lo = prmt(o0, o1, pk);
+    hi = prmt(o2, o3, pk);
+    if (vertical) transpose(lo, hi);
+}
+
+// all four afterstates: LEFT/RIGHT share one lookup per row, UP/DOWN one per column
+__device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ lr,
+                                         uint32_t (&rl)[4], uint32_t (&rh)[4])
+{
+    uint32_t tl = lo, th = hi;
+    transpose(tl, th);
+    const uint32_t r[8] = {lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16,
+                           tl & 0xFFFFu, tl >> 16, th & 0xFFFFu, th >> 16};
+    uint32_t o[8];
+    uint32_t any = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) any |= r[t];
+    if (__builtin_expect(any < kLrRows, 1)) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) o[t] = lr[r[t]];
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (r[t] < kLrRows) o[t] = lr[r[t]];
+            else o[t] = slow_row(r[t], false) | (slow_row(r[t], true) << 16);
+        }
+    }
+    rl[2] = prmt(o[0], o[1], 0x5410); rh[2] = prmt(o[2], o[3], 0x5410);     // LEFT
+    rl[3] = prmt(o[0], o[1], 0x7632); rh[3] = prmt(o[2], o[3], 0x7632);     // RIGHT
+    rl[0] = prmt(o[4], o[5], 0x5410); rh[0] = prmt(o[6], o[7], 0x5410);     // UP
+    rl[1] = prmt(o[4], o[5], 0x7632); rh[1] = prmt(o[6], o[7], 0x7632);     // DOWN
+    transpose(rl[0], rh[0]);
+    transpose(rl[1], rh[1]);
+}
+
 // ------------------------------------------------------------------ empties / spawn
 
-// bit 0 of every nibble = 1 where the nibble is zero
-__device__ __forceinline__ uint32_t zero_nibbles(uint32_t w)
+// bit 3 of every nibble = 1 where the nibble is zero: (y & 7) + 7 carries into bit 3 unless
+// the low three bits are zero; OR-ing y covers bit 3 itself.  LOP3, IADD, LOP3.
+__device__ __forceinline__ uint32_t zero_nibbles8(uint32_t y)
 {
-    uint32_t t = w | (w >> 1);
-    return ~(t | (t >> 2)) & 0x11111111u;
+    const uint32_t s = (y & 0x77777777u) + 0x77777777u;
+    return ~(s | y) & 0x88888888u;
 }
 
 // Exclusive prefix count of blanks per nibble (row-major = ascending nibble order, the
 // order of the reference's blank list, GameClient.py:109-114) and their total.
 struct Blanks {
-    uint32_t el, eh;    // blank flags
+    uint32_t el, eh;    // blank flags at bit 3 of each nibble
     uint32_t ql, qh;    // q[i] = number of blanks below nibble i (0..15, never overflows)
     uint32_t n;         // number of blanks (0..16)
 };
@@ -144,27 +233,47 @@ struct Blanks {
 __device__ __forceinline__ Blanks count_blanks(uint32_t lo, uint32_t hi)
 {
     Blanks b;
-    b.el = zero_nibbles(lo);
-    b.eh = zero_nibbles(hi);
-    // (eh:el) * 0x1111111111111110 : nibble i of the product = sum of flags below i
-    uint64_t p = (uint64_t)b.el * 0x11111110u;
+    b.el = zero_nibbles8(lo);
+    b.eh = zero_nibbles8(hi);
+    // flags/8 * 0x1111111111111110 == flags * 0x0222222222222222 : nibble i of the product
+    // = number of flags below nibble i
+    const uint64_t p = (uint64_t)b.el * 0x22222222u;
     b.ql = (uint32_t)p;
-    b.qh = (uint32_t)(p >> 32) + b.el * 0x11111111u + b.eh * 0x11111110u;
-    b.n = (b.qh >> 28) + (b.eh >> 28);
+    b.qh = (uint32_t)(p >> 32) + b.el * 0x02222222u + b.eh * 0x22222222u;
+    b.n = (b.qh >> 28) + (b.eh >> 31);
     return b;
 }
 
-// Put exponent `vexp` (1 or 2; 0 = nothing) into the k-th blank.
-__device__ __forceinline__ void place_tile(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
-                                           uint32_t vexp)
+// one-hot (bit 3 of the chosen nibble) mask of the k-th blank; zero if k >= n
+__device__ __forceinline__ void kth_blank(const Blanks &b, uint32_t k, uint32_t &sl, uint32_t &sh)
 {
     const uint32_t kk = k * 0x11111111u;
     const uint32_t xl = b.ql ^ kk, xh = b.qh ^ kk;       // zero nibble where q[i] == k
-    uint32_t tl = xl | (xl >> 1), th = xh | (xh >> 1);
-    const uint32_t sl = ~(tl | (tl >> 2)) & b.el;        // ... and the cell is blank: one bit
-    const uint32_t sh = ~(th | (th >> 2)) & b.eh;
-    lo += sl * vexp;
-    hi += sh * vexp;
+    const uint32_t tl = (xl & 0x77777777u) + 0x77777777u;
+    const uint32_t th = (xh & 0x77777777u) + 0x77777777u;
+    sl = ~(tl | xl) & b.el;                              // ... and the cell is blank
+    sh = ~(th | xh) & b.eh;
+}
+
+// Put exponent `vexp` (0 = nothing) into the k-th blank.
+__device__ __forceinline__ void place_tile(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
+                                           uint32_t vexp)
+{
+    uint32_t sl, sh;
+    kth_blank(b, k, sl, sh);
+    lo += (sl >> 3) * vexp;
+    hi += (sh >> 3) * vexp;
+}
+
+// The same for vexp in {0,1,2} given as v29 = vexp << 29: the high half of
+// (1 << (4i+3)) * (vexp << 29) is vexp << 4i, so the insert is one IMAD.HI per word.
+__device__ __forceinline__ void place_tile_v29(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
+                                               uint32_t v29)
+{
+    uint32_t sl, sh;
+    kth_blank(b, k, sl, sh);
+    lo += __umulhi(sl, v29);
+    hi += __umulhi(sh, v29);
 }
 
 // ------------------------------------------------------------------ game over

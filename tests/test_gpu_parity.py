@@ -137,7 +137,8 @@ def test_reset_vs_oracle(r48, orc):
 @pytest.mark.parametrize("mode", [0, 1])
 def test_step_vs_oracle(r48, orc, step, mode):
     n = 120001
-    b = random_boards(n, 7 + step % 5)
+    # the last third carries 16384 / 32768 tiles: rows outside the LR table (serial path)
+    b = np.concatenate([random_boards(80000, 7 + step % 5), random_boards(40001, 9, max_exp=15, p_zero=0.2)])
     a = np.random.default_rng(step).integers(0, 4, n).astype(np.uint8)
     env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE, reward_mode=mode)
     env.boards.copy_(boards_to_dev(b))
