@@ -194,6 +194,32 @@ def time_launches(torch, fn, iters):
     return start.elapsed_time(end) / iters       # ms per launch
 
 
+def time_graph(torch, fn, launches, replays=10):
+    """Capture `launches` calls of fn(i) into one CUDA graph (so that the Python/ctypes launch
+    cost, ~10 us per call, is out of the way) and time graph replays with CUDA events on the
+    replay stream.  Returns ms per launch."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(launches):                 # warm-up outside capture
+            fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(launches):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(replays):
+        g.replay()
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / (replays * launches)
+
+
 def bench_step_kernel(torch, r48, hbm_peak):
     """Config 2: 1M boards, one batched step per call, host-supplied actions already in HBM.
     Eight rotating buffer sets (8 x 22 MB = 176 MB > 126 MB L2) so every launch reads HBM."""
@@ -209,28 +235,27 @@ def bench_step_kernel(torch, r48, hbm_peak):
     out = torch.empty_like(boards_in)
     reward = torch.empty(n * sets, dtype=torch.int32, device="cuda")
     done = torch.empty(n * sets, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    pb, pa, po, pr, pd = (t.data_ptr() for t in (boards_in, actions, out, reward, done))
+
+    def cur():
+        return torch.cuda.current_stream().cuda_stream
 
     def launch(i):
         o = (i % sets) * n
-        r48._native.check(L.r48_step(boards_in[o:].data_ptr(), actions[o:].data_ptr(), out[o:].data_ptr(),
-                                     reward[o:].data_ptr(), done[o:].data_ptr(), n, SEED, o, 64, 0, None, stream))
-    for i in range(16):
-        launch(i)
-    ms = time_launches(torch, launch, 400)
+        r48._native.check(L.r48_step(pb + 8 * o, pa + o, po + 8 * o, pr + 4 * o, pd + o, n, SEED, o, 64, 0, None, cur()))
+    ms = time_graph(torch, launch, 64)
     alg_bytes = 22 * n
     gbs = alg_bytes / (ms * 1e-3) / 1e9
-    res = {"workload": "config 2: 2^20 boards, one step per call, actions in HBM, 8 rotating buffer sets (176 MB > L2)",
+    res = {"workload": "config 2: 2^20 boards, one step per call, actions in HBM, 8 rotating buffer sets (176 MB > L2), "
+                       "64 launches captured in a CUDA graph, timed with CUDA events over 10 replays",
            "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
     # the same kernel on one 16M-board launch (352 MB): launch latency amortised
     nbig = n * sets
     def launch_big(i):
-        r48._native.check(L.r48_step(boards_in.data_ptr(), actions.data_ptr(), out.data_ptr(), reward.data_ptr(),
-                                     done.data_ptr(), nbig, SEED, 0, 64, 0, None, stream))
-    launch_big(0)
-    ms_big = time_launches(torch, launch_big, 20)
+        r48._native.check(L.r48_step(pb, pa, po, pr, pd, nbig, SEED, 0, 64, 0, None, cur()))
+    ms_big = time_graph(torch, launch_big, 8)
     gbs_big = 22 * nbig / (ms_big * 1e-3) / 1e9
     res["at_8M_boards"] = {"us_per_launch": ms_big * 1e3, "GBps": gbs_big, "frac": gbs_big / hbm_peak,
                            "board_steps_per_sec": nbig / (ms_big * 1e-3)}
@@ -241,11 +266,8 @@ def bench_step_kernel(torch, r48, hbm_peak):
         wins = max(1, nbig // m)
         def launch_m(i, m=m, wins=wins):
             o = (i % wins) * m
-            r48._native.check(L.r48_step(boards_in[o:].data_ptr(), actions[o:].data_ptr(), out[o:].data_ptr(),
-                                         reward[o:].data_ptr(), done[o:].data_ptr(), m, SEED, o, 64, 0, None, stream))
-        for i in range(4):
-            launch_m(i)
-        t = time_launches(torch, launch_m, 100 if lg <= 21 else 20)
+            r48._native.check(L.r48_step(pb + 8 * o, pa + o, po + 8 * o, pr + 4 * o, pd + o, m, SEED, o, 64, 0, None, cur()))
+        t = time_graph(torch, launch_m, max(8, min(64, wins)))
         sweep["2^%d" % lg] = {"us": t * 1e3, "GBps": 22 * m / (t * 1e-3) / 1e9}
     res["size_sweep"] = sweep
     # end to end through the host-buffer entry point (pinned host memory, copies inside)
@@ -281,14 +303,11 @@ def bench_afterstates_kernel(torch, r48, hbm_peak):
     reward = torch.empty((n, 4), dtype=torch.int32, device="cuda")
     valid = torch.empty(n, dtype=torch.uint8, device="cuda")
     done = torch.empty(n, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    ptrs = tuple(t.data_ptr() for t in (boards, out, reward, valid, done))
 
     def launch(i):
-        r48._native.check(L.r48_afterstates(boards.data_ptr(), out.data_ptr(), reward.data_ptr(), valid.data_ptr(),
-                                            done.data_ptr(), n, 0, stream))
-    for i in range(3):
-        launch(i)
-    ms = time_launches(torch, launch, 20)
+        r48._native.check(L.r48_afterstates(*ptrs, n, 0, torch.cuda.current_stream().cuda_stream))
+    ms = time_graph(torch, launch, 8)
     alg_bytes = 58 * n
     gbs = alg_bytes / (ms * 1e-3) / 1e9
     return {"workload": "config 4: 2^23 boards x 4 afterstates + valid mask + done, 464 MB per launch (> L2)",

@@ -30,6 +30,30 @@ __device__ __forceinline__ uint32_t bsel(uint32_t m, uint32_t a, uint32_t b)
     return d;
 }
 
+// shared-window address of a shared-memory object, and table reads through it: the base is
+// computed once per kernel instead of once per lookup group, and every read is LDS [R + imm]
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// the same, made opaque so that ptxas keeps it in a register instead of re-deriving the
+// window base (S2UR CgaCtaId / UMOV / ULEA) in front of every group of lookups
+__device__ __forceinline__ uint32_t smem_u32_pinned(const void *p)
+{
+    uint32_t a = smem_u32(p), r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+
+// volatile: must not move above the mbarrier wait that publishes the staged tables
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // ------------------------------------------------------------------ Philox4x32-10
 // Salmon et al., SC'11.  The ten round keys depend only on the seed, so the host
 // precomputes them and they arrive as kernel parameters (constant bank operands).
@@ -155,15 +179,15 @@ __device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
     return out;
 }
 
-__device__ __forceinline__ uint32_t lr_lookup(const uint32_t *lr, uint32_t r, bool toward_high)
+// `lr` below is the shared-window byte address of the staged table (smem_u32)
+__device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool toward_high)
 {
-    if (r < kLrRows) return lr[r];
+    if (r < kLrRows) return lds_u32(lr + 4u * r);
     const uint32_t o = slow_row(r, toward_high);
     return o | (o << 16);
 }
 
-__device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t action,
-                                        const uint32_t *__restrict__ lr)
+__device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t lr)
 {
     const bool vertical = action < 2u;
     const bool toward_high = (action & 1u) != 0u;      // DOWN or RIGHT
@@ -171,7 +195,8 @@ __device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t act
     const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
     uint32_t o0, o1, o2, o3;
     if (__builtin_expect((r0 | r1 | r2 | r3) < kLrRows, 1)) {   // OR >= any row: conservative
-        o0 = lr[r0]; o1 = lr[r1]; o2 = lr[r2]; o3 = lr[r3];
+        o0 = lds_u32(lr + 4u * r0); o1 = lds_u32(lr + 4u * r1);
+        o2 = lds_u32(lr + 4u * r2); o3 = lds_u32(lr + 4u * r3);
     } else {
         o0 = lr_lookup(lr, r0, toward_high); o1 = lr_lookup(lr, r1, toward_high);
         o2 = lr_lookup(lr, r2, toward_high); o3 = lr_lookup(lr, r3, toward_high);
@@ -183,7 +208,7 @@ __device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t act
 }
 
 // all four afterstates: LEFT/RIGHT share one lookup per row, UP/DOWN one per column
-__device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, const uint32_t *__restrict__ lr,
+__device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, uint32_t lr,
                                          uint32_t (&rl)[4], uint32_t (&rh)[4])
 {
     uint32_t tl = lo, th = hi;
@@ -196,11 +221,11 @@ __device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, const uint32_
     for (int t = 0; t < 8; t++) any |= r[t];
     if (__builtin_expect(any < kLrRows, 1)) {
 #pragma unroll
-        for (int t = 0; t < 8; t++) o[t] = lr[r[t]];
+        for (int t = 0; t < 8; t++) o[t] = lds_u32(lr + 4u * r[t]);
     } else {
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            if (r[t] < kLrRows) o[t] = lr[r[t]];
+            if (r[t] < kLrRows) o[t] = lds_u32(lr + 4u * r[t]);
             else o[t] = slow_row(r[t], false) | (slow_row(r[t], true) << 16);
         }
     }
@@ -330,11 +355,6 @@ __device__ __forceinline__ uint32_t board_max_exp(uint32_t lo, uint32_t hi)
 // The 128 KB LEFT table (and the 64 KB merge table in reward mode) is copied global ->
 // shared by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) and signalled on an mbarrier,
 // so the copy overlaps the prologue (first loads, first Philox call) of each CTA.
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

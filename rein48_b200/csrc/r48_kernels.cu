@@ -187,7 +187,7 @@ struct StepParams {
 // flagged and the board passed through by selects (GameClient.py:254 raises there).
 template <bool REWARD, bool INJECT>
 __device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
-                                         uint32_t vw, const uint8_t *smem, int32_t &reward,
+                                         uint32_t vw, const uint8_t *smem, uint32_t lr, int32_t &reward,
                                          uint32_t &done, uint32_t &bad)
 {
     const uint32_t olo = lo, ohi = hi;
@@ -195,7 +195,7 @@ __device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t ac
     bad |= legal ? 0u : 1u;
     uint32_t rw = 0;
     if (REWARD) move_l16<true>(lo, hi, action, (const uint16_t *)smem, smem + kLeftBytes, rw);
-    else move_lr(lo, hi, action, (const uint32_t *)smem);
+    else move_lr(lo, hi, action, lr);
     if (!legal) { lo = olo; hi = ohi; rw = 0; }
     const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
     const Blanks b = count_blanks(lo, hi);
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     stage_tables<REWARD>(smem, p.tables, &bar);
+    const uint32_t lr = smem_u32_pinned(smem);
 
     bool ready = false;
     uint32_t bad = 0;
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         uint32_t lo1 = (uint32_t)bb.y, hi1 = (uint32_t)(bb.y >> 32);
         int32_t r0, r1;
         uint32_t d0, d1;
-        step_one<REWARD, INJECT>(lo0, hi0, aa.x, k0, v0, smem, r0, d0, bad);
-        step_one<REWARD, INJECT>(lo1, hi1, aa.y, k1, v1, smem, r1, d1, bad);
+        step_one<REWARD, INJECT>(lo0, hi0, aa.x, k0, v0, smem, lr, r0, d0, bad);
+        step_one<REWARD, INJECT>(lo1, hi1, aa.y, k1, v1, smem, lr, r1, d1, bad);
         ((ulonglong2 *)p.out)[j] = make_ulonglong2(((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
         if (p.reward) ((int2 *)p.reward)[j] = make_int2(r0, r1);
         if (p.done) ((uchar2 *)p.done)[j] = make_uchar2((uint8_t)d0, (uint8_t)d1);
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         if (!ready) { mbar_wait(&bar, 0); ready = true; }
         uint32_t lo0 = (uint32_t)b0, hi0 = (uint32_t)(b0 >> 32), d0;
         int32_t r0;
-        step_one<REWARD, INJECT>(lo0, hi0, a0, k0, v0, smem, r0, d0, bad);
+        step_one<REWARD, INJECT>(lo0, hi0, a0, k0, v0, smem, lr, r0, d0, bad);
         p.out[i] = ((uint64_t)hi0 << 32) | lo0;
         if (p.reward) p.reward[i] = r0;
         if (p.done) p.done[i] = (uint8_t)d0;
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     stage_tables<REWARD>(smem, p.tables, &bar);
+    const uint32_t lr = smem_u32_pinned(smem);
 
     bool ready = false;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
             }
         } else {
             uint32_t rl[4], rh[4];
-            move_all(lo, hi, (const uint32_t *)smem, rl, rh);
+            move_all(lo, hi, lr, rl, rh);
 #pragma unroll
             for (uint32_t a = 0; a < 4; a++) {
                 if ((rl[a] ^ lo) | (rh[a] ^ hi)) mask |= 1u << a;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
-    const uint32_t *lr = (const uint32_t *)smem;
+    const uint32_t lr = smem_u32_pinned(smem);
     stage_tables<false>(smem, p.tables, &bar);
 
     const uint32_t lane = threadIdx.x & 31u;
