@@ -111,7 +111,8 @@ def workload_config(args, n_gpus):
 # ---------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; only samples that fall inside the
+    timed region are kept."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -125,7 +126,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -133,9 +134,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
@@ -145,7 +146,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.06):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -172,15 +175,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def rollout_instr_per_step():
-    """SASS instructions one lane-step costs on the rollout kernel's steady-state path, taken
-    from the committed static count (profiles/rollout_sass.json, written by
-    tools/sass_stats.py --rollout-loop)."""
-    path = os.path.join(ROOT, "profiles", "rollout_sass.json")
+def rollout_issue_profile():
+    """Warp-instructions the rollout kernel issues per 32 env-steps, measured once by ncu
+    (profiles/rollout_issue.json, from smsp__inst_executed.sum of a 2^22-episode launch)."""
+    path = os.path.join(ROOT, "profiles", "rollout_issue.json")
     if os.path.exists(path):
-        d = json.load(open(path))
-        return float(d["instr_per_step"]), d.get("source", path)
-    return None, "profiles/rollout_sass.json missing"
+        return json.load(open(path))
+    return None
 
 
 def time_launches(torch, fn, iters):
@@ -383,20 +384,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                       # nvidia-smi needs ~0.3 s to start: begin before the warm-up
     for i in range(args.warmup):
         one_step(1000 + i)
     total_stats.zero_()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    wall0 = time.time()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
         one_step(i, ev[i])
     t_end.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
     elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
     k_ms = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps,
                          sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps,
@@ -442,18 +444,26 @@ def run_ours(args):
     rollout_ms, stats_ms, reduce_ms = (float(x) for x in k_ms.tolist())
     steps_per_launch = env_steps / args.steps / world          # per GPU
     per_gpu_rate = steps_per_launch / (rollout_ms * 1e-3)
-    instr, instr_src = rollout_instr_per_step()
+    prof = rollout_issue_profile()
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     roofline = {"bound": "issue", "kernel": "r48::rollout_kernel", "achieved": per_gpu_rate, "unit": "env-steps/s per GPU",
                 "peak": None, "frac": None, "traffic": None,
                 "ms_per_launch": rollout_ms, "share_of_step": rollout_ms / (elapsed_s * 1e3 / args.steps),
                 "algorithmic_bytes_per_launch": 12 * n,
-                "hbm_GBps_of_outputs": 12 * n / (rollout_ms * 1e-3) / 1e9}
-    if instr:
-        peak = 148 * 4 * 32 * sm_mhz * 1e6 / instr
-        roofline.update({"peak": peak, "frac": per_gpu_rate / peak, "instr_per_step": instr, "instr_source": instr_src,
-                         "peak_formula": "148 SMs x 4 schedulers x 32 lanes x sm_mhz (median under load) / "
-                                         "SASS instructions per env-step"})
+                "hbm_GBps_of_outputs": 12 * n / (rollout_ms * 1e-3) / 1e9,
+                "why_not_hbm": "12 B per EPISODE (0.08 B per env-step): HBM traffic is ~0; north_star names integer "
+                               "issue slots as this kernel's bound"}
+    if prof:
+        w = float(prof["warp_instr_per_32_steps"])
+        peak = 148 * 4 * sm_mhz * 1e6 * 32 / w
+        roofline.update({"peak": peak, "frac": per_gpu_rate / peak,
+                         "warp_instr_per_32_steps": w, "instr_source": prof.get("source"),
+                         "ipc_per_sm_implied": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6),
+                         "peak_formula": "148 SMs x 4 schedulers x sm_mhz (median under load) x 32 lanes / "
+                                         "warp-instructions per 32 env-steps (ncu); frac = issue-slot utilisation",
+                         "traffic": prof.get("dram_bytes_per_launch"),
+                         "traffic_note": "dram bytes of the profiled 2^22-episode launch (most of its 50 MB of "
+                                         "outputs is still in L2 when the kernel ends)"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
