@@ -225,11 +225,15 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
 
     bool ready = false;
     uint32_t bad = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32-bit indices (the host splits batches of 2^30 boards and more): every array address is
+    // one IMAD.WIDE from the index
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = (uint32_t)p.n;
     const bool odd = (p.tick & 1u) != 0u;
-    const int64_t pairs = VEC ? (p.n >> 1) : 0;
-    for (int64_t j = tid; j < pairs; j += stride) {
+    const uint32_t pairs = VEC ? (n >> 1) : 0u;
+    if (VEC)
+    for (uint32_t j = tid; j < pairs; j += stride) {
         const ulonglong2 bb = ((const ulonglong2 *)p.in)[j];
         const uchar2 aa = ((const uchar2 *)p.action)[j];
         uint32_t k0, k1, v0, v1;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             k0 = kk.x; k1 = kk.y; v0 = vv.x; v1 = vv.y;
         } else {
             uint32_t w[4];
-            const uint64_t id0 = p.board_base + (uint64_t)(2 * j);
+            const uint64_t id0 = p.board_base + 2ull * j;
             philox4x32_10((uint32_t)id0, (uint32_t)(id0 >> 32), p.tick >> 1, 0u, p.keys, w);
             k0 = odd ? w[2] : w[0]; v0 = odd ? w[3] : w[1];
             const uint64_t id1 = id0 + 1;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         if (p.done) ((uchar2 *)p.done)[j] = make_uchar2((uint8_t)d0, (uint8_t)d1);
     }
     // boards not covered by pairs: everything (scalar kernel) or the odd last one
-    for (int64_t i = 2 * pairs + tid; i < p.n; i += stride) {
+    for (uint32_t i = 2u * pairs + tid; i < n; i += stride) {
         const uint64_t b0 = p.in[i];
         const uint32_t a0 = p.action[i];
         uint32_t k0, v0;
@@ -304,8 +308,8 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
     const uint32_t lr = smem_u32_pinned(smem);
 
     bool ready = false;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const uint32_t stride = gridDim.x * blockDim.x, n = (uint32_t)p.n;     // host splits batches >= 2^30
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t b = p.in[i];
         if (!ready) { mbar_wait(&bar, 0); ready = true; }
         const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
                 res[a] = ((uint64_t)rh[a] << 32) | rl[a];
             }
         }
-        ulonglong2 *o = (ulonglong2 *)(p.out + 4 * i);
+        ulonglong2 *o = (ulonglong2 *)p.out + 2ull * i;
         o[0] = make_ulonglong2(res[0], res[1]);
         o[1] = make_ulonglong2(res[2], res[3]);
         if (p.reward)
@@ -652,23 +656,33 @@ int check_n(int64_t n)
     return R48_OK;
 }
 
+constexpr int64_t kChunk = (int64_t)1 << 30;     // boards per launch (kernels index with 32 bits)
+
 template <bool INJECT>
-int launch_step(const StepParams &p, int reward_mode, const DeviceState &d, cudaStream_t s)
+int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, cudaStream_t s)
 {
-    const bool vec = aligned(p.in, 16) && aligned(p.out, 16) && aligned(p.action, 2) &&
-                     (!p.reward || aligned(p.reward, 8)) && (!p.done || aligned(p.done, 2)) &&
-                     (!INJECT || (aligned(p.spawn_k, 2) && aligned(p.spawn_exp, 2)));
-    const int64_t units = vec ? (p.n + 1) / 2 : p.n;
-    const int grid = grid_for(units, kThreads, d.sms, 1);
-    const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
-    if (reward_mode) {
-        if (vec) step_kernel<true, INJECT, true><<<grid, kThreads, smem, s>>>(p);
-        else step_kernel<true, INJECT, false><<<grid, kThreads, smem, s>>>(p);
-    } else {
-        if (vec) step_kernel<false, INJECT, true><<<grid, kThreads, smem, s>>>(p);
-        else step_kernel<false, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+    for (int64_t off = 0; off < whole.n; off += kChunk) {
+        StepParams p = whole;
+        p.n = whole.n - off < kChunk ? whole.n - off : kChunk;
+        p.in += off; p.action += off; p.out += off; p.board_base += (uint64_t)off;
+        if (p.reward) p.reward += off;
+        if (p.done) p.done += off;
+        if (INJECT) { p.spawn_k += off; p.spawn_exp += off; }
+        const bool vec = aligned(p.in, 16) && aligned(p.out, 16) && aligned(p.action, 2) &&
+                         (!p.reward || aligned(p.reward, 8)) && (!p.done || aligned(p.done, 2)) &&
+                         (!INJECT || (aligned(p.spawn_k, 2) && aligned(p.spawn_exp, 2)));
+        const int64_t units = vec ? (p.n + 1) / 2 : p.n;
+        const int grid = grid_for(units, kThreads, d.sms, 1);
+        const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
+        if (reward_mode) {
+            if (vec) step_kernel<true, INJECT, true><<<grid, kThreads, smem, s>>>(p);
+            else step_kernel<true, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+        } else {
+            if (vec) step_kernel<false, INJECT, true><<<grid, kThreads, smem, s>>>(p);
+            else step_kernel<false, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+        }
+        CK(cudaGetLastError());
     }
-    CK(cudaGetLastError());
     return R48_OK;
 }
 
@@ -832,13 +846,17 @@ int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t 
         return fail(R48_ERR_ALIGN, "r48_afterstates: in needs 8-byte, out/reward 16-byte alignment");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
-    AfterParams p{in, out, reward, valid, done, n, d->tables()};
-    const int grid = grid_for(n, kThreads, d->sms, 1);
-    if (reward_mode)
-        afterstates_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
-    else
-        afterstates_kernel<false><<<grid, kThreads, kLrBytes, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
+    for (int64_t off = 0; off < n; off += kChunk) {
+        const int64_t m = n - off < kChunk ? n - off : kChunk;
+        AfterParams p{in + off, out + 4 * off, reward ? reward + 4 * off : nullptr, valid ? valid + off : nullptr,
+                      done ? done + off : nullptr, m, d->tables()};
+        const int grid = grid_for(m, kThreads, d->sms, 1);
+        if (reward_mode)
+            afterstates_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
+        else
+            afterstates_kernel<false><<<grid, kThreads, kLrBytes, (cudaStream_t)stream>>>(p);
+        CK(cudaGetLastError());
+    }
     return R48_OK;
 }
 
