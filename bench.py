@@ -292,6 +292,28 @@ def bench_step_kernel(torch, r48, hbm_peak):
     return res
 
 
+def bench_env_step_kernel(torch, r48, hbm_peak):
+    """policy-in-the-loop step -- per-env counters, auto-reset, float32 readout fused
+    into the epilogue.  2^20 envs, 8 rotating env sets (8 x 102 MB); actions already in HBM."""
+    n, sets = 1 << 20, 8
+    envs = [r48.BatchedGame(n, seed=SEED + s, board_base=s * n) for s in range(sets)]
+    acts = [torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8) for _ in range(sets)]
+    for e, a in zip(envs, acts):
+        for _ in range(48):
+            e.env_step(a)
+
+    def launch(i):
+        envs[i % sets].env_step(acts[i % sets])
+    ms = time_graph(torch, launch, 32)
+    alg_bytes = 102 * n          # board 8+8, action 1, steps 4+4, episodes 4+4, reward 4, done 1, obs 64
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    return {"workload": "8(f).1: 2^20 envs, Game.step with per-env counters + auto-reset + fused float32 [n,4,4] "
+                        "readout, 8 rotating env sets",
+            "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+
+
 def bench_afterstates_kernel(torch, r48, hbm_peak):
     """Config 4: 8M boards, all 4 moves + game-over per board; 464 MB per launch (> L2)."""
     n = 1 << 23
@@ -491,7 +513,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         ks = bench_step_kernel(torch, r48, hbm_peak)
         ka = bench_afterstates_kernel(torch, r48, hbm_peak)
-        line["kernels"] = {"step_1M": ks, "afterstates_8M": ka}
+        ke = bench_env_step_kernel(torch, r48, hbm_peak)
+        line["kernels"] = {"step_1M": ks, "afterstates_8M": ka, "env_step_1M": ke}
         line["roofline_hbm"] = dict(ks["roofline"], kernel="r48::step_kernel", peak_source=peak_src)
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline

@@ -88,6 +88,21 @@ int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *
                       const uint8_t *spawn_exp, uint64_t *out, int32_t *reward, uint8_t *done,
                       int64_t n, int reward_mode, int32_t *status, void *stream);
 
+/* Vectorised-environment step for a policy in the loop (the a3c.py:187-243 / ddpg.py:12-70
+ * worker loops, batched): every env carries its own counters, so envs may be at different
+ * points of different episodes.  Env i plays global board id
+ *     board_base + i + episodes[i] * id_stride          (id_stride >= n, e.g. the world batch)
+ * and this call is tick steps[i]+1 of it.  After Game.step, steps[i] is incremented; if the
+ * game is over and auto_reset != 0 the final board is kept in final_boards[i] (optional), the
+ * env is reset in place (Game.reset of its next episode id: episodes[i]++, steps[i] = 0) and
+ * done[i] = 1 is returned together with the NEW episode's first board, gym-vector style.
+ * obs (optional) = float32 [n][4][4] readout of the board left in boards[i]: tile values
+ * (obs_mode 0, np.array(state) of a3c.py:195) or exponents (obs_mode 1). */
+int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
+                 int32_t *reward, uint8_t *done, float *obs, int obs_mode, uint64_t *final_boards,
+                 int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
+                 int reward_mode, int auto_reset, int32_t *status, void *stream);
+
 /* Game.random_fill_grid alone (GameClient.py:102-127) with injected draws: put exponent
  * spawn_exp[i] into the spawn_k[i]-th blank (row-major) of boards[i]; k >= n_blank leaves
  * the board as it is (a full board is returned unchanged, GameClient.py:117-118). */

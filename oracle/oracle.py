@@ -71,6 +71,9 @@ def lib():
     L.orc_step_batch.restype = C.c_int
     L.orc_step_injected_batch.argtypes = [u64p, u8p, u8p, u8p, u64p, i32p, u8p, C.c_int64, C.c_int]
     L.orc_step_injected_batch.restype = C.c_int
+    L.orc_env_step_batch.argtypes = [u64p, u8p, u32p, u32p, i32p, u8p, u64p, C.c_int64, C.c_uint64,
+                                     C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+    L.orc_env_step_batch.restype = C.c_int
     L.orc_afterstates_batch.argtypes = [u64p, u64p, i32p, u8p, u8p, C.c_int64, C.c_int]
     L.orc_afterstates_batch.restype = None
     L.orc_decode_batch_f32.argtypes = [u64p, f32p, C.c_int64, C.c_int]
@@ -202,6 +205,24 @@ def step_injected_batch(boards, actions, spawn_k, spawn_exp, reward_mode=0):
     if rc != 0:
         raise ValueError("bad action")
     return out, reward, done
+
+
+def env_step_batch(boards, actions, steps, episodes, seed, board_base, id_stride, reward_mode=0,
+                   auto_reset=True):
+    """In place on copies: -> (boards, steps, episodes, reward, done, final_boards)"""
+    boards = np.array(boards, np.uint64)
+    steps = np.array(steps, np.uint32)
+    episodes = np.array(episodes, np.uint32)
+    n = boards.size
+    reward = np.zeros(n, np.int32)
+    done = np.zeros(n, np.uint8)
+    final = np.zeros(n, np.uint64)
+    rc = lib().orc_env_step_batch(boards, np.ascontiguousarray(actions, np.uint8), steps, episodes, reward,
+                                  done, final, n, int(seed), int(board_base), int(id_stride),
+                                  int(reward_mode), int(bool(auto_reset)))
+    if rc != 0:
+        raise ValueError("bad action")
+    return boards, steps, episodes, reward, done, final
 
 
 def afterstates_batch(boards, reward_mode=0):

@@ -107,6 +107,30 @@ class BatchedGame:
         self.steps += 1
         return self.boards, self.reward, self.done
 
+    # -- vectorised-env form: per-env counters, auto-reset, fused observation
+    def env_step(self, actions, auto_reset=True, obs=True, log2=False, id_stride=None):
+        """Game.step for every env with its OWN tick/episode counters; finished games are reset
+        in place when auto_reset (done[i] = 1 then comes with the new episode's first board,
+        the finished board is kept in `self.final_boards`).  Returns (obs or boards, reward,
+        done).  Do not mix with step() on the same object: that one keys all boards by one
+        shared step counter."""
+        a = as_actions(actions, self.device)
+        if a.numel() != self.n:
+            raise ValueError("expected %d actions, got %d" % (self.n, a.numel()))
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "env_steps"):
+                self.env_steps = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+                self.env_episodes = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+                self.final_boards = torch.zeros(self.n, dtype=torch.int64, device=self.device)
+                self.obs = torch.empty((self.n, 4, 4), dtype=torch.float32, device=self.device)
+            _native.check(self._lib.r48_env_step(
+                self.boards.data_ptr(), a.data_ptr(), self.env_steps.data_ptr(), self.env_episodes.data_ptr(),
+                self.reward.data_ptr(), self.done.data_ptr(), self.obs.data_ptr() if obs else None,
+                int(bool(log2)), self.final_boards.data_ptr(), self.n, self.seed, self.board_base,
+                int(id_stride if id_stride is not None else self.n), self.reward_mode, int(bool(auto_reset)),
+                self.status.data_ptr(), _stream(self.device)))
+        return (self.obs if obs else self.boards), self.reward, self.done
+
     def check_actions(self):
         """Synchronising check that no step() so far saw an action outside 0..3; raises the
         ValueError the reference raises at GameClient.py:254."""

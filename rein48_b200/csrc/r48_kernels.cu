@@ -287,6 +287,85 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
     if (!ready) mbar_wait(&bar, 0);          // never leave with the bulk copy in flight
 }
 
+// ------------------------------------------------------------------ vectorised env step
+
+struct EnvParams {
+    uint64_t *boards;
+    const uint8_t *action;
+    uint32_t *steps;
+    uint32_t *episodes;
+    int32_t *reward;             // may be NULL
+    uint8_t *done;               // may be NULL
+    float *obs;                  // may be NULL
+    uint64_t *final_boards;      // may be NULL
+    int32_t *status;             // may be NULL
+    uint32_t n;
+    uint64_t board_base;
+    uint64_t id_stride;
+    int obs_log2;
+    int auto_reset;
+    PhiloxKeys keys;
+    Tables tables;
+};
+
+// Game.step with per-env tick / episode counters, optional auto-reset and the float readout
+// fused into the epilogue (one pass over the board instead of step + decode).
+template <bool REWARD>
+__global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    stage_tables<REWARD>(smem, p.tables, &bar);
+    const uint32_t lr = smem_u32_pinned(smem);
+
+    bool ready = false;
+    uint32_t bad = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const uint64_t b = p.boards[i];
+        const uint32_t a = p.action[i];
+        uint32_t st = p.steps[i], ep = p.episodes[i];
+        uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
+        uint32_t aw, vw;
+        draw_words(id, st + 1u, p.keys, aw, vw);
+        if (!ready) { mbar_wait(&bar, 0); ready = true; }
+        uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d;
+        int32_t r;
+        step_one<REWARD, false>(lo, hi, a, aw, vw, smem, lr, r, d, bad);
+        st += 1u;
+        if (d && p.auto_reset) {                 // rare: a lane's game ended
+            if (p.final_boards) p.final_boards[i] = ((uint64_t)hi << 32) | lo;
+            ep += 1u; st = 0u;
+            id = p.board_base + i + (uint64_t)ep * p.id_stride;
+            draw_words(id, 0u, p.keys, aw, vw);
+            lo = 0u; hi = 0u;
+            const Blanks bl = count_blanks(lo, hi);
+            place_tile(lo, hi, bl, __umulhi(aw << 2, bl.n), vw < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+        }
+        p.boards[i] = ((uint64_t)hi << 32) | lo;
+        p.steps[i] = st;
+        p.episodes[i] = ep;
+        if (p.reward) p.reward[i] = r;
+        if (p.done) p.done[i] = (uint8_t)d;
+        if (p.obs) {
+            float4 *o = (float4 *)p.obs + 4ull * i;
+#pragma unroll
+            for (int row = 0; row < 4; row++) {
+                const uint32_t w = (row < 2 ? lo : hi) >> (16 * (row & 1));
+                float v[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t e = (w >> (4 * t)) & 15u;
+                    v[t] = p.obs_log2 ? (float)e : (float)((1u << e) & ~1u);
+                }
+                o[row] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    if (bad && p.status) atomicOr(p.status, 1);
+    if (!ready) mbar_wait(&bar, 0);
+}
+
 // ------------------------------------------------------------------ afterstates
 
 struct AfterParams {
@@ -606,6 +685,8 @@ int ensure_device(int dev, DeviceState **out)
         CK(opt_in_smem(step_kernel<true, false, false>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(step_kernel<true, true, true>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(step_kernel<true, true, false>, kLeftBytes + kMergeBytes));
+        CK(opt_in_smem(env_step_kernel<false>, kLrBytes));
+        CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
         CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(rollout_kernel, kLrBytes));
@@ -787,6 +868,39 @@ int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *
     StepParams p{in, action, spawn_k, spawn_exp, out, reward, done, status, n, 0ull,
                  0u, make_keys(0), d->tables()};
     return launch_step<true>(p, reward_mode, *d, (cudaStream_t)stream);
+}
+
+int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
+                 int32_t *reward, uint8_t *done, float *obs, int obs_mode, uint64_t *final_boards,
+                 int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
+                 int reward_mode, int auto_reset, int32_t *status, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_env_step: reward_mode must be 0 or 1");
+    if (obs_mode != 0 && obs_mode != 1) return fail(R48_ERR_ARG, "r48_env_step: obs_mode must be 0 or 1");
+    if (n == 0) return R48_OK;
+    if (!boards || !action || !steps || !episodes) return fail(R48_ERR_NULL, "r48_env_step: boards/action/steps/episodes is NULL");
+    if ((uint64_t)n > id_stride) return fail(R48_ERR_ARG, "r48_env_step: id_stride must be >= n");
+    if (!aligned(boards, 8) || !aligned(steps, 4) || !aligned(episodes, 4) || (reward && !aligned(reward, 4)) ||
+        (obs && !aligned(obs, 16)) || (final_boards && !aligned(final_boards, 8)) || (status && !aligned(status, 4)))
+        return fail(R48_ERR_ALIGN, "r48_env_step: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    for (int64_t off = 0; off < n; off += kChunk) {
+        const int64_t m = n - off < kChunk ? n - off : kChunk;
+        EnvParams p{boards + off, action + off, steps + off, episodes + off, reward ? reward + off : nullptr,
+                    done ? done + off : nullptr, obs ? obs + 16 * off : nullptr,
+                    final_boards ? final_boards + off : nullptr, status, (uint32_t)m,
+                    board_base + (uint64_t)off, id_stride, obs_mode, auto_reset, make_keys(seed), d->tables()};
+        const int grid = grid_for(m, kThreads, d->sms, 1);
+        if (reward_mode)
+            env_step_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
+        else
+            env_step_kernel<false><<<grid, kThreads, kLrBytes, (cudaStream_t)stream>>>(p);
+        CK(cudaGetLastError());
+    }
+    return R48_OK;
 }
 
 int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,

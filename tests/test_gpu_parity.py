@@ -184,6 +184,34 @@ def test_spawn_vs_oracle(r48, orc):
         assert orc.encode(m) == int(got[i])
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_env_step_autoreset_vs_oracle(r48, orc, mode):
+    """Policy-in-the-loop stepping: per-env tick/episode counters, auto-reset, fused readout.
+    300 steps of a fixed pseudo-random policy take most envs through several episodes."""
+    n = 3001
+    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE, reward_mode=mode)
+    boards = orc.reset_batch(n, SEED, BIG_BASE)
+    assert (to_u64(env.boards) == boards).all()
+    steps = np.zeros(n, np.uint32)
+    eps = np.zeros(n, np.uint32)
+    rng = np.random.default_rng(4)
+    finished = 0
+    for t in range(300):
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        obs, reward, done = env.env_step(dev(a), log2=bool(t & 1))
+        boards, steps, eps, o_r, o_d, o_f = orc.env_step_batch(boards, a, steps, eps, SEED, BIG_BASE, n, mode)
+        assert (to_u64(env.boards) == boards).all(), t
+        assert (reward.cpu().numpy() == o_r).all() and (done.cpu().numpy() == o_d).all()
+        assert (env.env_steps.cpu().numpy().view(np.uint32) == steps).all()
+        assert (env.env_episodes.cpu().numpy().view(np.uint32) == eps).all()
+        d = o_d.astype(bool)
+        assert (to_u64(env.final_boards)[d] == o_f[d]).all()
+        assert (obs.cpu().numpy() == orc.decode_batch(boards, "float32", bool(t & 1))).all()
+        finished += int(d.sum())
+    assert finished > n          # every env went through more than one episode on average
+    env.check_actions()
+
+
 # ------------------------------------------------------------------ fused rollout
 
 def test_rollout_bit_exact_vs_oracle(r48, orc):
