@@ -379,6 +379,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialisation attribute
+// may start (and stage its tables) while the previous kernel in the stream is still draining;
+// it must call pdl_wait() before touching anything the previous kernel wrote.
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(

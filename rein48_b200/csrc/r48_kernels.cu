@@ -101,6 +101,10 @@ __device__ __forceinline__ void stage_tables(uint8_t *smem, const Tables &g, uin
                 bulk_g2s(smem + off, (const uint8_t *)g.lr + off, 32768u, bar);
         }
     }
+    // The tables never change after r48_init, so staging them does not depend on the previous
+    // kernel in the stream; everything after this line may.
+    pdl_launch_dependents();
+    pdl_wait();
 }
 
 template <bool REWARD>
@@ -739,6 +743,24 @@ int check_n(int64_t n)
 
 constexpr int64_t kChunk = (int64_t)1 << 30;     // boards per launch (kernels index with 32 bits)
 
+// Launch with programmatic stream serialisation: the CTAs of this kernel may be scheduled, and
+// stage their tables, as SMs of the previous kernel in the stream free up (see stage_tables).
+template <typename P>
+cudaError_t launch_pdl(void (*kernel)(P), int grid, int block, uint32_t smem, cudaStream_t s, const P &params)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 template <bool INJECT>
 int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, cudaStream_t s)
 {
@@ -756,13 +778,12 @@ int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, 
         const int grid = grid_for(units, kThreads, d.sms, 1);
         const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
         if (reward_mode) {
-            if (vec) step_kernel<true, INJECT, true><<<grid, kThreads, smem, s>>>(p);
-            else step_kernel<true, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+            if (vec) CK(launch_pdl(step_kernel<true, INJECT, true>, grid, kThreads, smem, s, p));
+            else CK(launch_pdl(step_kernel<true, INJECT, false>, grid, kThreads, smem, s, p));
         } else {
-            if (vec) step_kernel<false, INJECT, true><<<grid, kThreads, smem, s>>>(p);
-            else step_kernel<false, INJECT, false><<<grid, kThreads, smem, s>>>(p);
+            if (vec) CK(launch_pdl(step_kernel<false, INJECT, true>, grid, kThreads, smem, s, p));
+            else CK(launch_pdl(step_kernel<false, INJECT, false>, grid, kThreads, smem, s, p));
         }
-        CK(cudaGetLastError());
     }
     return R48_OK;
 }
@@ -895,10 +916,9 @@ int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint3
                     board_base + (uint64_t)off, id_stride, obs_mode, auto_reset, make_keys(seed), d->tables()};
         const int grid = grid_for(m, kThreads, d->sms, 1);
         if (reward_mode)
-            env_step_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
+            CK(launch_pdl(env_step_kernel<true>, grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream, p));
         else
-            env_step_kernel<false><<<grid, kThreads, kLrBytes, (cudaStream_t)stream>>>(p);
-        CK(cudaGetLastError());
+            CK(launch_pdl(env_step_kernel<false>, grid, kThreads, kLrBytes, (cudaStream_t)stream, p));
     }
     return R48_OK;
 }
@@ -966,10 +986,9 @@ int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t 
                       done ? done + off : nullptr, m, d->tables()};
         const int grid = grid_for(m, kThreads, d->sms, 1);
         if (reward_mode)
-            afterstates_kernel<true><<<grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream>>>(p);
+            CK(launch_pdl(afterstates_kernel<true>, grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream, p));
         else
-            afterstates_kernel<false><<<grid, kThreads, kLrBytes, (cudaStream_t)stream>>>(p);
-        CK(cudaGetLastError());
+            CK(launch_pdl(afterstates_kernel<false>, grid, kThreads, kLrBytes, (cudaStream_t)stream, p));
     }
     return R48_OK;
 }
@@ -1008,8 +1027,7 @@ int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_b
     RolloutParams p{final_boards, lengths, (unsigned long long *)workspace, (uint64_t)n, board_base,
                     make_keys(seed), d->tables()};
     const int grid = grid_for(n, kThreads, d->sms, 1);
-    rollout_kernel<<<grid, kThreads, kLrBytes, s>>>(p);
-    CK(cudaGetLastError());
+    CK(launch_pdl(rollout_kernel, grid, kThreads, kLrBytes, s, p));
     if (stats) return r48_episode_stats(final_boards, lengths, n, stats, stream);
     return R48_OK;
 }
