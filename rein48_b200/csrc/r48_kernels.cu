@@ -654,6 +654,8 @@ struct DeviceState {
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // D2H of finished chunks overlaps the next chunk's kernel
+    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
 };
 
 DeviceState g_dev[kMaxDevices];
@@ -791,6 +793,11 @@ int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, 
 int arena_reserve(DeviceState &d, size_t bytes)
 {
     if (!d.stream) CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    if (!d.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&d.chunk_done[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&d.chunk_done[1], cudaEventDisableTiming));
+    }
     if (d.arena_bytes >= bytes) return R48_OK;
     if (d.arena) CK(cudaFree(d.arena));
     d.arena = nullptr;
@@ -1179,14 +1186,29 @@ int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *fi
     uint64_t *d_fb = (uint64_t *)(d->arena + o_fb);
     uint32_t *d_len = (uint32_t *)(d->arena + o_len);
     uint64_t *d_stats = (uint64_t *)(d->arena + o_stats);
-    cudaStream_t s = d->stream;
+    cudaStream_t s = d->stream, c = d->copy_stream;
     if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
-    rc = r48_rollout(n, seed, board_base, d_fb, d_len, stats ? d_stats : nullptr, d->arena + o_ws, s);
-    if (rc) return rc;
-    if (final_boards) CK(cudaMemcpyAsync(final_boards, d_fb, nb * 8, cudaMemcpyDeviceToHost, s));
-    if (lengths) CK(cudaMemcpyAsync(lengths, d_len, nb * 4, cudaMemcpyDeviceToHost, s));
+    // Large batches go in chunks of 2^23 episodes: the per-episode results of chunk i travel to
+    // the host on the copy stream while chunk i+1 is being played.
+    const int64_t chunk = n > ((int64_t)1 << 24) ? ((int64_t)1 << 23) : n;
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        rc = r48_rollout(m, seed, board_base + (uint64_t)off, d_fb + off, d_len + off,
+                         stats ? d_stats : nullptr, d->arena + o_ws, s);
+        if (rc) return rc;
+        if (final_boards || lengths) {
+            CK(cudaEventRecord(d->chunk_done[slot], s));
+            CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
+            if (final_boards)
+                CK(cudaMemcpyAsync(final_boards + off, d_fb + off, (size_t)m * 8, cudaMemcpyDeviceToHost, c));
+            if (lengths)
+                CK(cudaMemcpyAsync(lengths + off, d_len + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+        }
+    }
     if (stats) CK(cudaMemcpyAsync(stats, d_stats, R48_STATS_WORDS * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(c));
     return R48_OK;
 }
 
@@ -1199,6 +1221,8 @@ int r48_shutdown(void)
         DeviceGuard g(dev);
         if (d.arena) cudaFree(d.arena);
         if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        for (int e = 0; e < 2; e++) if (d.chunk_done[e]) cudaEventDestroy(d.chunk_done[e]);
         if (d.left) cudaFree(d.left);
         if (d.merges) cudaFree(d.merges);
         if (d.lr) cudaFree(d.lr);

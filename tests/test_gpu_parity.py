@@ -263,6 +263,20 @@ def test_rollout_host_entry(r48, orc):
     assert (out.stats.numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
 
 
+def test_rollout_host_chunked(r48, orc):
+    """n > 2^24 goes in 2^23-episode chunks with the D2H copies overlapped: same episodes as one
+    device launch, and the tail chunk checked against the oracle."""
+    n = (1 << 24) + 12345
+    out = r48.random_rollouts_host(n, seed=9, board_base=5)
+    dev_res = r48.random_rollouts(n, seed=9, board_base=5)
+    assert (out.final_boards.cuda() == dev_res.final_boards).all()
+    assert (out.lengths.cuda() == dev_res.lengths).all()
+    assert (out.stats.cuda() == dev_res.stats).all()
+    fb, ln = orc.rollout(12345, 9, 5 + (1 << 24), threads=4)
+    assert (out.final_boards.numpy().view(np.uint64)[1 << 24:] == fb).all()
+    assert (out.lengths.numpy().view(np.uint32)[1 << 24:] == ln).all()
+
+
 def test_step_host_entry(r48, orc):
     n = 70001
     b = random_boards(n, 77)
