@@ -433,8 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
 struct RolloutParams {
     uint64_t *final_boards;
     uint32_t *lengths;
-    unsigned long long *counter;     // next unassigned episode
-    uint64_t n;
+    unsigned int *counter;           // next unassigned episode (32-bit: the host splits launches)
+    uint32_t n;
     uint64_t board_base;
     PhiloxKeys keys;
     Tables tables;
@@ -460,9 +460,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     stage_tables<false>(smem, p.tables, &bar);
 
     const uint32_t lane = threadIdx.x & 31u;
-    constexpr uint64_t kNone = ~0ull;
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
     uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
-    uint64_t ep = kNone;
+    uint32_t ep = kNone;
     bool live = true;           // the queue may still have work for this lane
     mbar_wait(&bar, 0);
 
@@ -475,11 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
             }
             const uint32_t want = __ballot_sync(kFull, fin);
             const uint32_t leader = __ffs(want) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(want));
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(p.counter, (unsigned int)__popc(want));
             base = __shfl_sync(kFull, base, leader);
             if (fin) {
-                const uint64_t mine = base + __popc(want & ((1u << lane) - 1u));
+                const uint32_t mine = base + __popc(want & ((1u << lane) - 1u));
                 if (mine < p.n) {
                     ep = mine; lo = 0; hi = 0; tick = 0; failed = 0;
                 } else {                       // queue empty: park (failed stays 3, live off)
@@ -1030,11 +1030,15 @@ int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_b
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
-    RolloutParams p{final_boards, lengths, (unsigned long long *)workspace, (uint64_t)n, board_base,
-                    make_keys(seed), d->tables()};
-    const int grid = grid_for(n, kThreads, d->sms, 1);
-    CK(launch_pdl(rollout_kernel, grid, kThreads, kLrBytes, s, p));
+    constexpr int64_t kRolloutChunk = (int64_t)1 << 31;      // the kernel's episode queue is 32-bit
+    for (int64_t off = 0; off < n; off += kRolloutChunk) {
+        const int64_t m = n - off < kRolloutChunk ? n - off : kRolloutChunk;
+        CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
+        RolloutParams p{final_boards + off, lengths + off, (unsigned int *)workspace, (uint32_t)m,
+                        board_base + (uint64_t)off, make_keys(seed), d->tables()};
+        const int grid = grid_for(m, kThreads, d->sms, 1);
+        CK(launch_pdl(rollout_kernel, grid, kThreads, kLrBytes, s, p));
+    }
     if (stats) return r48_episode_stats(final_boards, lengths, n, stats, stream);
     return R48_OK;
 }
