@@ -130,6 +130,18 @@ int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t 
 int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
                 uint32_t *lengths, uint64_t *stats, void *workspace, void *stream);
 
+/* The same loop with another built-in policy (extension):
+ *   R48_POLICY_RANDOM         control/rand.py (what r48_rollout runs)
+ *   R48_POLICY_GREEDY_BLANKS  1-ply greedy: among the moves that change the board take the one
+ *                             whose afterstate has the most blank cells; candidates are visited
+ *                             in the order r, r+1, r+2, r+3 (mod 4), r = the tick's random
+ *                             action, first best wins; spawn and game over as in Game.step. */
+#define R48_POLICY_RANDOM        0
+#define R48_POLICY_GREEDY_BLANKS 1
+int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy,
+                       uint64_t *final_boards, uint32_t *lengths, uint64_t *stats, void *workspace,
+                       void *stream);
+
 /* Episode statistics of finished games, accumulated into stats[R48_STATS_WORDS]. */
 int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int64_t n,
                       uint64_t *stats, void *stream);

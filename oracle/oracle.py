@@ -84,6 +84,8 @@ def lib():
     L.orc_play_episode.restype = C.c_uint32
     L.orc_rollout.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, u64p, u32p]
     L.orc_rollout.restype = None
+    L.orc_rollout_greedy.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, u64p, u32p]
+    L.orc_rollout_greedy.restype = None
     L.orc_rollout_mt.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, u64p, u32p, C.c_int]
     L.orc_rollout_mt.restype = C.c_int
     L.orc_stats_words.argtypes = []
@@ -257,6 +259,13 @@ def rollout(n, seed, board_base=0, threads=1):
         lib().orc_rollout(n, int(seed), int(board_base), fb, ln)
     else:
         lib().orc_rollout_mt(n, int(seed), int(board_base), fb, ln, int(threads))
+    return fb, ln
+
+
+def rollout_greedy(n, seed, board_base=0):
+    fb = np.zeros(n, np.uint64)
+    ln = np.zeros(n, np.uint32)
+    lib().orc_rollout_greedy(n, int(seed), int(board_base), fb, ln)
     return fb, ln
 
 

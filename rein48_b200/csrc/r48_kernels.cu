@@ -452,6 +452,15 @@ struct RolloutParams {
 // the board was dead since the last tick that changed it, and that tick is the episode
 // length.  This replaces a ~20-instruction neighbour test per tick by a few predicated ops
 // at the price of ~3 extra no-op ticks per episode (2 %); outputs are identical.
+enum : int { kPolicyRandom = 0, kPolicyGreedyBlanks = 1 };
+
+// number of blank cells of a board (selection only; the spawn uses count_blanks)
+__device__ __forceinline__ uint32_t blank_count(uint32_t lo, uint32_t hi)
+{
+    return __popc(zero_nibbles8(lo) | (zero_nibbles8(hi) >> 1));
+}
+
+template <int POLICY>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -461,13 +470,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
+    // random policy: `failed` collects the axes seen to fail on the current full board (3 = over);
+    // greedy policy: `failed` is simply set to 3 when no move changes the board
     uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
     uint32_t ep = kNone;
     bool live = true;           // the queue may still have work for this lane
     mbar_wait(&bar, 0);
 
     for (;;) {
-        const bool fin = live && failed == 3u;          // both axes failed: episode over
+        const bool fin = live && failed == 3u;          // episode over
         if (__any_sync(kFull, fin)) {
             if (fin && ep != kNone) {
                 p.final_boards[ep] = ((uint64_t)hi << 32) | lo;
@@ -496,17 +507,39 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
-            const uint32_t olo = lo, ohi = hi;
-            move_lr(lo, hi, aw >> 30, lr);
-            // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
-            const bool changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
+            bool changed;
+            if (POLICY == kPolicyRandom) {
+                const uint32_t olo = lo, ohi = hi;
+                move_lr(lo, hi, aw >> 30, lr);
+                // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
+                changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
+            } else {
+                // all four afterstates; key = blanks * 4 + (3 - rotation offset), -1 if the move
+                // changes nothing: the maximum is the greedy choice with the first-best tie rule
+                uint32_t rl[4], rh[4];
+                move_all(lo, hi, lr, rl, rh);
+                const uint32_t r = aw >> 30;
+                int best = -1;
+                uint32_t bl = lo, bh = hi;
+#pragma unroll
+                for (uint32_t a = 0; a < 4; a++) {
+                    const bool valid = ((rl[a] ^ lo) | (rh[a] ^ hi)) != 0u;
+                    const int key = valid ? (int)(blank_count(rl[a], rh[a]) * 4u + (3u - ((a - r) & 3u))) : -1;
+                    if (key > best) { best = key; bl = rl[a]; bh = rh[a]; }
+                }
+                changed = best >= 0 || tick == 0u;
+                if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
+                lo = bl; hi = bh;
+            }
             const Blanks b = count_blanks(lo, hi);
             const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
             place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), v29);
-            // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
-            const uint32_t axis = 2u - (aw >> 31);
-            failed = changed ? 0u : (b.n == 0u ? (failed | axis) : failed);
-            last_change = changed ? tick : last_change;
+            if (POLICY == kPolicyRandom) {
+                // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
+                const uint32_t axis = 2u - (aw >> 31);
+                failed = changed ? 0u : (b.n == 0u ? (failed | axis) : failed);
+                last_change = changed ? tick : last_change;
+            }
             tick++;
         }
     }
@@ -695,7 +728,8 @@ int ensure_device(int dev, DeviceState **out)
         CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
         CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(rollout_kernel, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyRandom>, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks>, kLrBytes));
         CK(cudaSetDevice(prev));
         d.ready = true;
     }
@@ -1017,11 +1051,14 @@ int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int
     return R48_OK;
 }
 
-int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
-                uint32_t *lengths, uint64_t *stats, void *workspace, void *stream)
+int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy,
+                       uint64_t *final_boards, uint32_t *lengths, uint64_t *stats, void *workspace,
+                       void *stream)
 {
     int rc = check_n(n);
     if (rc) return rc;
+    if (policy != R48_POLICY_RANDOM && policy != R48_POLICY_GREEDY_BLANKS)
+        return fail(R48_ERR_ARG, "r48_rollout_policy: unknown policy");
     if (n == 0) return R48_OK;
     if (!final_boards || !lengths || !workspace) return fail(R48_ERR_NULL, "r48_rollout: NULL pointer");
     if (!aligned(final_boards, 8) || !aligned(lengths, 4) || !aligned(workspace, 8) ||
@@ -1037,10 +1074,20 @@ int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_b
         RolloutParams p{final_boards + off, lengths + off, (unsigned int *)workspace, (uint32_t)m,
                         board_base + (uint64_t)off, make_keys(seed), d->tables()};
         const int grid = grid_for(m, kThreads, d->sms, 1);
-        CK(launch_pdl(rollout_kernel, grid, kThreads, kLrBytes, s, p));
+        if (policy == R48_POLICY_RANDOM)
+            CK(launch_pdl(rollout_kernel<kPolicyRandom>, grid, kThreads, kLrBytes, s, p));
+        else
+            CK(launch_pdl(rollout_kernel<kPolicyGreedyBlanks>, grid, kThreads, kLrBytes, s, p));
     }
     if (stats) return r48_episode_stats(final_boards, lengths, n, stats, stream);
     return R48_OK;
+}
+
+int r48_rollout(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                uint32_t *lengths, uint64_t *stats, void *workspace, void *stream)
+{
+    return r48_rollout_policy(n, seed, board_base, R48_POLICY_RANDOM, final_boards, lengths, stats,
+                              workspace, stream);
 }
 
 int r48_scores(const uint64_t *boards, uint32_t *score, uint8_t *max_exp, int64_t n, void *stream)

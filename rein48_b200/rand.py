@@ -43,10 +43,14 @@ class RolloutBuffers:
                                          device=self.device)
 
 
-def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_stats=True):
+POLICIES = {"random": 0, "greedy_blanks": 1}
+
+
+def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_stats=True, policy="random"):
     """Play global episodes board_base .. board_base+n-1 to game over with the uniform random
-    policy.  Returns RolloutResult(final_boards int64[n], lengths int32[n], stats int64[4120]);
-    everything stays on the device and the call does not synchronise."""
+    policy (or policy="greedy_blanks": 1-ply greedy on the number of blank cells, random
+    tie-break order).  Returns RolloutResult(final_boards int64[n], lengths int32[n],
+    stats int64[4120]); everything stays on the device and the call does not synchronise."""
     if buffers is None:
         buffers = RolloutBuffers(n, device)
     if n > buffers.n:
@@ -56,8 +60,9 @@ def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_s
     with torch.cuda.device(dev):
         if with_stats:
             buffers.stats.zero_()
-        _native.check(L.r48_rollout(
-            int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), buffers.final_boards.data_ptr(),
+        _native.check(L.r48_rollout_policy(
+            int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), POLICIES[policy],
+            buffers.final_boards.data_ptr(),
             buffers.lengths.data_ptr(), buffers.stats.data_ptr() if with_stats else None,
             buffers.workspace.data_ptr(), _stream(dev)))
     return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats)

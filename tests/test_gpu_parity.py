@@ -223,6 +223,20 @@ def test_rollout_bit_exact_vs_oracle(r48, orc):
     assert (res.stats.cpu().numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
 
 
+def test_greedy_rollout_bit_exact_vs_oracle(r48, orc):
+    """1-ply greedy policy fused in the rollout kernel == the oracle's episodes."""
+    n = 6000
+    res = r48.random_rollouts(n, seed=SEED, board_base=BIG_BASE, policy="greedy_blanks")
+    fb, ln = orc.rollout_greedy(n, SEED, BIG_BASE)
+    assert (to_u64(res.final_boards) == fb).all()
+    assert (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
+    assert (res.stats.cpu().numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
+    _, _, valid, done = r48.afterstates(res.final_boards)
+    assert bool((valid == 0).all()) and bool((done == 1).all())
+    rnd = r48.EpisodeStats(r48.random_rollouts(n, seed=SEED, board_base=BIG_BASE).stats.clone())
+    assert r48.EpisodeStats(res.stats).mean_score > 1.3 * rnd.mean_score
+
+
 def test_rollout_equals_repeated_step(r48):
     """the fused kernel is the step kernel applied tick by tick with the Philox actions"""
     n = 4096
