@@ -1174,19 +1174,30 @@ int r48_step_host(const uint64_t *in, const uint8_t *action, uint64_t *out, int3
     int32_t *d_rew = (int32_t *)(d->arena + o_rew);
     uint8_t *d_done = d->arena + o_done;
     int32_t *d_status = (int32_t *)(d->arena + o_status);
-    cudaStream_t s = d->stream;
-    CK(cudaMemcpyAsync(d_board, in, nb * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_act, action, nb, cudaMemcpyHostToDevice, s));
+    cudaStream_t s = d->stream, c = d->copy_stream;
     CK(cudaMemsetAsync(d_status, 0, 4, s));
-    rc = r48_step(d_board, d_act, d_board, reward ? d_rew : nullptr, done ? d_done : nullptr, n, seed,
-                  board_base, step, reward_mode, d_status, s);
-    if (rc) return rc;
+    // 3-stage pipeline over chunks of 2^18 boards: H2D + kernel of chunk i+1 on the compute stream
+    // overlap the D2H of chunk i on the copy stream (PCIe is full duplex)
+    const int64_t chunk = n > ((int64_t)1 << 19) ? ((int64_t)1 << 18) : n;
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
+        const size_t m = (size_t)(n - off < chunk ? n - off : chunk);
+        CK(cudaMemcpyAsync(d_board + off, in + off, m * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_act + off, action + off, m, cudaMemcpyHostToDevice, s));
+        rc = r48_step(d_board + off, d_act + off, d_board + off, reward ? d_rew + off : nullptr,
+                      done ? d_done + off : nullptr, (int64_t)m, seed, board_base + (uint64_t)off, step,
+                      reward_mode, d_status, s);
+        if (rc) return rc;
+        CK(cudaEventRecord(d->chunk_done[slot], s));
+        CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
+        CK(cudaMemcpyAsync(out + off, d_board + off, m * 8, cudaMemcpyDeviceToHost, c));
+        if (reward) CK(cudaMemcpyAsync(reward + off, d_rew + off, m * 4, cudaMemcpyDeviceToHost, c));
+        if (done) CK(cudaMemcpyAsync(done + off, d_done + off, m, cudaMemcpyDeviceToHost, c));
+    }
     int32_t h_status = 0;
-    CK(cudaMemcpyAsync(out, d_board, nb * 8, cudaMemcpyDeviceToHost, s));
-    if (reward) CK(cudaMemcpyAsync(reward, d_rew, nb * 4, cudaMemcpyDeviceToHost, s));
-    if (done) CK(cudaMemcpyAsync(done, d_done, nb, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&h_status, d_status, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(c));
     if (h_status & 1) return fail(R48_ERR_ACTION, "r48_step_host: action byte > 3");
     return R48_OK;
 }

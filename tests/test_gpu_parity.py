@@ -291,8 +291,8 @@ def test_rollout_host_chunked(r48, orc):
     assert (out.lengths.numpy().view(np.uint32)[1 << 24:] == ln).all()
 
 
-def test_step_host_entry(r48, orc):
-    n = 70001
+@pytest.mark.parametrize("n", [70001, (1 << 19) + (1 << 18) + 3])      # single launch / chunked pipeline
+def test_step_host_entry(r48, orc, n):
     b = random_boards(n, 77)
     a = np.random.default_rng(3).integers(0, 4, n).astype(np.uint8)
     out = np.zeros(n, np.uint64)
