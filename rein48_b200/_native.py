@@ -17,7 +17,7 @@ DEPS = [SRC, os.path.join(_PKG, "csrc", "r48_device.cuh"), os.path.join(_ROOT, "
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "186",
 ]
 
 OK, ERR_NULL, ERR_ALIGN, ERR_ARG, ERR_CUDA, ERR_ACTION = 0, -1, -2, -3, -4, -5
