@@ -509,6 +509,15 @@ def run_ours(args):
         line["rollout_config3"] = {"workload": "config 3: 2^24 episodes, 1 GPU (rollout + statistics kernels)",
                                    "ms_per_step": ms3, "env_steps_per_sec": st3.steps / (ms3 * 1e-3),
                                    "episodes_per_sec": n3 / (ms3 * 1e-3)}
+        # the same fused kernel with the 1-ply greedy (most blanks) policy
+        r48.random_rollouts(n3, seed=SEED, buffers=b3, policy="greedy_blanks")
+        msg = time_launches(torch, lambda i: r48.random_rollouts(n3, seed=SEED + i, buffers=b3,
+                                                                  policy="greedy_blanks"), 2)
+        stg = r48.EpisodeStats(b3.stats)
+        line["rollout_greedy_blanks"] = {"workload": "2^24 episodes, 1-ply greedy on blank count (4 afterstates per step)",
+                                         "ms_per_step": msg, "env_steps_per_sec": stg.steps / (msg * 1e-3),
+                                         "mean_episode_length": stg.mean_length, "mean_score": stg.mean_score,
+                                         "max_tile": stg.max_tile}
         b3 = None
         torch.cuda.empty_cache()
         ks = bench_step_kernel(torch, r48, hbm_peak)
