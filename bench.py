@@ -520,6 +520,22 @@ def run_ours(args):
                                          "max_tile": stg.max_tile}
         b3 = None
         torch.cuda.empty_cache()
+        # data generation: every (state, action) of 2^22 random episodes (two passes: play, then replay + write)
+        nt = 1 << 22
+        r48.rollout_trajectories(nt, seed=SEED)                 # warm the allocator
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        tr = r48.rollout_trajectories(nt, seed=SEED + 1)
+        e1.record()
+        torch.cuda.synchronize()
+        mst = e0.elapsed_time(e1)
+        line["trajectories"] = {"workload": "2^22 random episodes, all transitions kept (9 B per step)",
+                                "transitions": tr.boards.numel(), "ms": mst,
+                                "transitions_per_sec": tr.boards.numel() / (mst * 1e-3),
+                                "GBps_written": 9 * tr.boards.numel() / (mst * 1e-3) / 1e9}
+        tr = None
+        torch.cuda.empty_cache()
         ks = bench_step_kernel(torch, r48, hbm_peak)
         ka = bench_afterstates_kernel(torch, r48, hbm_peak)
         ke = bench_env_step_kernel(torch, r48, hbm_peak)

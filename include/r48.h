@@ -142,6 +142,18 @@ int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy
                        uint64_t *final_boards, uint32_t *lengths, uint64_t *stats, void *workspace,
                        void *stream);
 
+/* Trajectories of the same episodes (what the learners buffer per step: a3c.py:205-209,
+ * ddpg.py:29-31 -- and without ddpg.py:31's aliasing of state and next_state): replays
+ * episodes board_base..+n-1 under `policy` -- draws are counter-based, so an episode is a pure
+ * function of (seed, id) -- and writes, for step t = 1..lengths[i] of episode i,
+ *     traj_boards[offsets[i] + t-1]  = the board BEFORE the step (the state the policy saw)
+ *     traj_actions[offsets[i] + t-1] = the action taken
+ * lengths[] comes from r48_rollout(_policy) with the same arguments, offsets[] is its exclusive
+ * prefix sum; the board after the last step is final_boards[i] of that call. */
+int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int policy,
+                             const uint32_t *lengths, const uint64_t *offsets, uint64_t *traj_boards,
+                             uint8_t *traj_actions, void *workspace, void *stream);
+
 /* Episode statistics of finished games, accumulated into stats[R48_STATS_WORDS]. */
 int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int64_t n,
                       uint64_t *stats, void *stream);

@@ -86,6 +86,9 @@ def lib():
     L.orc_rollout.restype = None
     L.orc_rollout_greedy.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, u64p, u32p]
     L.orc_rollout_greedy.restype = None
+    L.orc_rollout_trajectories.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, C.c_int, i64p, u64p, u8p,
+                                           C.c_int64, u64p]
+    L.orc_rollout_trajectories.restype = C.c_int64
     L.orc_rollout_mt.argtypes = [C.c_int64, C.c_uint64, C.c_uint64, u64p, u32p, C.c_int]
     L.orc_rollout_mt.restype = C.c_int
     L.orc_stats_words.argtypes = []
@@ -267,6 +270,20 @@ def rollout_greedy(n, seed, board_base=0):
     ln = np.zeros(n, np.uint32)
     lib().orc_rollout_greedy(n, int(seed), int(board_base), fb, ln)
     return fb, ln
+
+
+def rollout_trajectories(n, seed, board_base=0, policy=0, capacity=None):
+    """-> (offsets int64[n+1], boards u64[T], actions u8[T], final_boards u64[n])"""
+    capacity = capacity or 1200 * n + 4096
+    offsets = np.zeros(n + 1, np.int64)
+    boards = np.zeros(capacity, np.uint64)
+    actions = np.zeros(capacity, np.uint8)
+    final = np.zeros(n, np.uint64)
+    total = lib().orc_rollout_trajectories(n, int(seed), int(board_base), int(policy), offsets, boards,
+                                           actions, capacity, final)
+    if total < 0:
+        raise MemoryError("trajectory capacity too small")
+    return offsets, boards[:total], actions[:total], final
 
 
 def episode_stats(final_boards, lengths, stats=None):

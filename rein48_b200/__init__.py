@@ -9,13 +9,13 @@ from . import _native
 from ._native import R48Error, build
 from .batched import BatchedGame, afterstates, blank_counts, decode, encode, scores, spawn_injected
 from .game import Game, action_code
-from .rand import (Rand, RolloutBuffers, RolloutResult, play, random_rollouts, random_rollouts_host,
-                   sharded_rollouts)
+from .rand import (Rand, RolloutBuffers, RolloutResult, Trajectories, play, random_rollouts,
+                   random_rollouts_host, rollout_trajectories, sharded_rollouts)
 from .stats import STATS_WORDS, EpisodeStats, allreduce_stats, shard_range
 
 __all__ = [
     "BatchedGame", "Game", "Rand", "play", "random_rollouts", "random_rollouts_host",
-    "sharded_rollouts", "RolloutBuffers", "RolloutResult", "EpisodeStats", "allreduce_stats",
+    "sharded_rollouts", "rollout_trajectories", "Trajectories", "RolloutBuffers", "RolloutResult", "EpisodeStats", "allreduce_stats",
     "shard_range", "afterstates", "decode", "encode", "scores", "blank_counts", "spawn_injected",
     "action_code", "build", "R48Error", "STATS_WORDS",
 ]

@@ -27,7 +27,7 @@ ROLLOUT_WORKSPACE_BYTES = 256
 # every symbol include/r48.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "r48_version", "r48_last_error", "r48_init", "r48_debug_tables_host", "r48_reset", "r48_step",
-    "r48_step_injected", "r48_env_step", "r48_spawn_injected", "r48_spawn", "r48_blank_counts", "r48_afterstates", "r48_rollout", "r48_rollout_policy", "r48_episode_stats", "r48_scores",
+    "r48_step_injected", "r48_env_step", "r48_spawn_injected", "r48_spawn", "r48_blank_counts", "r48_afterstates", "r48_rollout", "r48_rollout_policy", "r48_rollout_trajectories", "r48_episode_stats", "r48_scores",
     "r48_decode_f32", "r48_decode_i32", "r48_encode_i32", "r48_step_host", "r48_afterstates_host",
     "r48_rollout_host", "r48_shutdown",
 )
@@ -89,6 +89,7 @@ def lib():
         L.r48_afterstates.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
         L.r48_rollout.argtypes = [i64, u64, u64, vp, vp, vp, vp, vp]
         L.r48_rollout_policy.argtypes = [i64, u64, u64, i32, vp, vp, vp, vp, vp]
+        L.r48_rollout_trajectories.argtypes = [i64, u64, u64, i32, vp, vp, vp, vp, vp, vp]
         L.r48_episode_stats.argtypes = [vp, vp, i64, vp, vp]
         L.r48_scores.argtypes = [vp, vp, vp, i64, vp]
         L.r48_decode_f32.argtypes = [vp, vp, i64, i32, vp]

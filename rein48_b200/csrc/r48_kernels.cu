@@ -438,6 +438,10 @@ struct RolloutParams {
     uint64_t board_base;
     PhiloxKeys keys;
     Tables tables;
+    // trajectory replay (RECORD kernels): lengths[] is then an INPUT, final_boards is unused
+    const uint64_t *traj_offsets;    // [n] first slot of each episode (exclusive prefix sum of lengths)
+    uint64_t *traj_boards;           // board BEFORE step t of the episode, t = 1..length
+    uint8_t *traj_actions;           // the action taken at that step
 };
 
 // One lane = one episode at a time, board in two registers; when its game ends the lane
@@ -460,7 +464,10 @@ __device__ __forceinline__ uint32_t blank_count(uint32_t lo, uint32_t hi)
     return __popc(zero_nibbles8(lo) | (zero_nibbles8(hi) >> 1));
 }
 
-template <int POLICY>
+// RECORD: second pass of r48_rollout_trajectories.  Counter-based draws make an episode
+// replayable from (seed, id) alone, so the variable-length trajectories are written by playing
+// every episode again once the lengths (hence the output offsets) are known.
+template <int POLICY, bool RECORD>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -474,13 +481,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     // greedy policy: `failed` is simply set to 3 when no move changes the board
     uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
     uint32_t ep = kNone;
+    uint32_t rec_len = 0;       // RECORD: length of the episode being replayed ...
+    uint64_t rec_off = 0;       // ... and its first output slot
     bool live = true;           // the queue may still have work for this lane
     mbar_wait(&bar, 0);
 
     for (;;) {
         const bool fin = live && failed == 3u;          // episode over
         if (__any_sync(kFull, fin)) {
-            if (fin && ep != kNone) {
+            if (!RECORD && fin && ep != kNone) {
                 p.final_boards[ep] = ((uint64_t)hi << 32) | lo;
                 p.lengths[ep] = last_change;
             }
@@ -493,8 +502,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 const uint32_t mine = base + __popc(want & ((1u << lane) - 1u));
                 if (mine < p.n) {
                     ep = mine; lo = 0; hi = 0; tick = 0; failed = 0;
+                    if (RECORD) { rec_len = p.lengths[mine]; rec_off = p.traj_offsets[mine]; }
                 } else {                       // queue empty: park (failed stays 3, live off)
-                    live = false; ep = kNone;
+                    live = false; ep = kNone; rec_len = 0;
                 }
             }
             if (!__any_sync(kFull, live)) break;
@@ -507,9 +517,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
+            const uint32_t olo = lo, ohi = hi;
+            uint32_t taken = aw >> 30;
             bool changed;
             if (POLICY == kPolicyRandom) {
-                const uint32_t olo = lo, ohi = hi;
                 move_lr(lo, hi, aw >> 30, lr);
                 // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
                 changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
@@ -525,11 +536,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 for (uint32_t a = 0; a < 4; a++) {
                     const bool valid = ((rl[a] ^ lo) | (rh[a] ^ hi)) != 0u;
                     const int key = valid ? (int)(blank_count(rl[a], rh[a]) * 4u + (3u - ((a - r) & 3u))) : -1;
-                    if (key > best) { best = key; bl = rl[a]; bh = rh[a]; }
+                    if (key > best) { best = key; bl = rl[a]; bh = rh[a]; taken = a; }
                 }
                 changed = best >= 0 || tick == 0u;
                 if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
                 lo = bl; hi = bh;
+            }
+            if (RECORD && tick - 1u < rec_len) {         // steps 1..length of a live episode
+                p.traj_boards[rec_off + (tick - 1u)] = ((uint64_t)ohi << 32) | olo;
+                p.traj_actions[rec_off + (tick - 1u)] = (uint8_t)taken;
             }
             const Blanks b = count_blanks(lo, hi);
             const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
@@ -728,8 +743,10 @@ int ensure_device(int dev, DeviceState **out)
         CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
         CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
         CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyRandom>, kLrBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks>, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyRandom, false>, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, false>, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyRandom, true>, kLrBytes));
+        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, true>, kLrBytes));
         CK(cudaSetDevice(prev));
         d.ready = true;
     }
@@ -1072,14 +1089,46 @@ int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy
         const int64_t m = n - off < kRolloutChunk ? n - off : kRolloutChunk;
         CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
         RolloutParams p{final_boards + off, lengths + off, (unsigned int *)workspace, (uint32_t)m,
-                        board_base + (uint64_t)off, make_keys(seed), d->tables()};
+                        board_base + (uint64_t)off, make_keys(seed), d->tables(), nullptr, nullptr, nullptr};
         const int grid = grid_for(m, kThreads, d->sms, 1);
         if (policy == R48_POLICY_RANDOM)
-            CK(launch_pdl(rollout_kernel<kPolicyRandom>, grid, kThreads, kLrBytes, s, p));
+            CK(launch_pdl(rollout_kernel<kPolicyRandom, false>, grid, kThreads, kLrBytes, s, p));
         else
-            CK(launch_pdl(rollout_kernel<kPolicyGreedyBlanks>, grid, kThreads, kLrBytes, s, p));
+            CK(launch_pdl(rollout_kernel<kPolicyGreedyBlanks, false>, grid, kThreads, kLrBytes, s, p));
     }
     if (stats) return r48_episode_stats(final_boards, lengths, n, stats, stream);
+    return R48_OK;
+}
+
+int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int policy,
+                             const uint32_t *lengths, const uint64_t *offsets, uint64_t *traj_boards,
+                             uint8_t *traj_actions, void *workspace, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (policy != R48_POLICY_RANDOM && policy != R48_POLICY_GREEDY_BLANKS)
+        return fail(R48_ERR_ARG, "r48_rollout_trajectories: unknown policy");
+    if (n == 0) return R48_OK;
+    if (!lengths || !offsets || !traj_boards || !traj_actions || !workspace)
+        return fail(R48_ERR_NULL, "r48_rollout_trajectories: NULL pointer");
+    if (!aligned(lengths, 4) || !aligned(offsets, 8) || !aligned(traj_boards, 8) || !aligned(workspace, 8))
+        return fail(R48_ERR_ALIGN, "r48_rollout_trajectories: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    constexpr int64_t kRolloutChunk = (int64_t)1 << 31;
+    for (int64_t off = 0; off < n; off += kRolloutChunk) {
+        const int64_t m = n - off < kRolloutChunk ? n - off : kRolloutChunk;
+        CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
+        RolloutParams p{nullptr, const_cast<uint32_t *>(lengths) + off, (unsigned int *)workspace, (uint32_t)m,
+                        board_base + (uint64_t)off, make_keys(seed), d->tables(), offsets + off, traj_boards,
+                        traj_actions};
+        const int grid = grid_for(m, kThreads, d->sms, 1);
+        if (policy == R48_POLICY_RANDOM)
+            CK(launch_pdl(rollout_kernel<kPolicyRandom, true>, grid, kThreads, kLrBytes, s, p));
+        else
+            CK(launch_pdl(rollout_kernel<kPolicyGreedyBlanks, true>, grid, kThreads, kLrBytes, s, p));
+    }
     return R48_OK;
 }
 

@@ -68,6 +68,31 @@ def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_s
     return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats)
 
 
+Trajectories = namedtuple("Trajectories", "offsets boards actions final_boards lengths stats")
+
+
+def rollout_trajectories(n, seed=0, device="cuda", board_base=0, policy="random"):
+    """Play n episodes and keep every transition: data generation for the learners (the
+    reference's README: "run tens of thousands of games on the GPU to make data").
+    Returns Trajectories(offsets int64[n+1], boards int64[T], actions uint8[T], final_boards,
+    lengths, stats) with T = total steps; steps of episode i are offsets[i]..offsets[i+1]-1,
+    boards[] holds the state BEFORE each step, the state after the last one is final_boards[i]."""
+    res = random_rollouts(n, seed=seed, device=device, board_base=board_base, policy=policy)
+    dev = res.final_boards.device
+    L = _native.lib()
+    with torch.cuda.device(dev):
+        offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(res.lengths, 0, out=offsets[1:])
+        total = int(offsets[-1].item())
+        boards = torch.empty(total, dtype=torch.int64, device=dev)
+        actions = torch.empty(total, dtype=torch.uint8, device=dev)
+        ws = torch.zeros(_native.ROLLOUT_WORKSPACE_BYTES // 8, dtype=torch.int64, device=dev)
+        _native.check(L.r48_rollout_trajectories(
+            int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), POLICIES[policy], res.lengths.data_ptr(),
+            offsets.data_ptr(), boards.data_ptr(), actions.data_ptr(), ws.data_ptr(), _stream(dev)))
+    return Trajectories(offsets, boards, actions, res.final_boards, res.lengths, res.stats)
+
+
 def sharded_rollouts(n_total, seed=0, device=None, buffers=None, group=None):
     """One rank's share of n_total episodes + the SUM all-reduce of the statistics vector.
     Call from every rank of an initialised torch.distributed job (or standalone)."""
@@ -116,4 +141,5 @@ def play(game, control="rand", show_state=False, show_result=False):
 
 
 __all__ = ["Rand", "RolloutBuffers", "RolloutResult", "random_rollouts", "sharded_rollouts",
+           "rollout_trajectories", "Trajectories",
            "random_rollouts_host", "play", "EpisodeStats", "scores"]

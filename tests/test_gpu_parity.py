@@ -237,6 +237,28 @@ def test_greedy_rollout_bit_exact_vs_oracle(r48, orc):
     assert r48.EpisodeStats(res.stats).mean_score > 1.3 * rnd.mean_score
 
 
+@pytest.mark.parametrize("policy,code", [("random", 0), ("greedy_blanks", 1)])
+def test_rollout_trajectories_vs_oracle(r48, orc, policy, code):
+    """Every (state, action) of every episode: the GPU's replay pass against the oracle."""
+    n = 3000
+    tr = r48.rollout_trajectories(n, seed=SEED, board_base=BIG_BASE, policy=policy)
+    off, boards, actions, final = orc.rollout_trajectories(n, SEED, BIG_BASE, code)
+    assert (tr.offsets.cpu().numpy() == off).all()
+    assert (to_u64(tr.boards) == boards).all()
+    assert (tr.actions.cpu().numpy() == actions).all()
+    assert (to_u64(tr.final_boards) == final).all()
+    # consistency on the GPU alone: stepping the recorded state with the recorded action gives
+    # the next recorded state up to the spawned tile (same tile mass + 2 or 4)
+    sc, _ = r48.scores(tr.boards)
+    nxt = torch.cat([tr.boards[1:], tr.final_boards[-1:]])
+    last = torch.zeros_like(tr.boards, dtype=torch.bool)
+    last[tr.offsets[1:] - 1] = True
+    nxt[last] = tr.final_boards
+    sn, _ = r48.scores(nxt)
+    gain = sn - sc
+    assert bool(((gain == 0) | (gain == 2) | (gain == 4)).all())
+
+
 def test_rollout_equals_repeated_step(r48):
     """the fused kernel is the step kernel applied tick by tick with the Philox actions"""
     n = 4096
