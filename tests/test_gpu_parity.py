@@ -414,3 +414,13 @@ def test_game_adapter_surface(r48, golden):
     assert r48.Game.random_fill_grid([r[:] for r in full]) == full      # GameClientTest.py:43-44
     gp = r48.Game(rng="philox", seed=5, board_id=3)
     assert r48.play(gp, "rand") == np.sum(gp.state_matrix)
+
+
+def test_cli_plays_the_reference_seed(r48, golden, capsys):
+    """`python -m rein48_b200 -c rand -v n --seed 0` == `random.seed(0); main.py -c rand`."""
+    from rein48_b200.__main__ import main
+    fp = golden("episodes_ref.npz")["fingerprint"]
+    assert main(["-c", "rand", "-v", "n", "--seed", "0"]) == 0
+    assert capsys.readouterr().out.strip().endswith("score %d" % fp[0][1])
+    assert main(["--episodes", "1000", "--seed", "3"]) == 0
+    assert '"episodes": 1000' in capsys.readouterr().out
