@@ -4,11 +4,13 @@
 //             -Xcompiler -fPIC -shared -o libr48.so r48_kernels.cu
 //
 // Kernel inventory (DESIGN.md has the roofline of each):
-//   build_tables_kernel   65536-entry LEFT-move row table + merge table, once per device
+//   build_tables_kernel   row tables (LR: LEFT|RIGHT per row; L16 + merges), once per device
 //   reset_kernel          Game.reset                       GameClient.py:33-38
 //   step_kernel           Game.step                        GameClient.py:40-51
+//   env_step_kernel       step + auto-reset + readout      a3c.py:187-243, ddpg.py:12-70 (worker loops)
 //   afterstates_kernel    4 x Game.update_matrix + over    GameClient.py:129-254, 65-94
 //   rollout_kernel        main.play(control="rand")        main.py:36-42 + rand.py:9-11
+//                         <policy, record>: random | greedy-blanks; play | replay-and-record
 //   stats/scores/decode/encode  readout                     main.py:48, a3c.py:195,205
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,7 +23,7 @@
 
 namespace r48 {
 
-constexpr int kThreads = 1024;                 // one CTA per SM (the 128 KB table fills smem)
+constexpr int kThreads = 1024;                    // one CTA per SM (the table fills its shared memory)
 constexpr uint32_t kLeftBytes = 65536 * 2;        // reward-mode tables: LEFT rows (u16) ...
 constexpr uint32_t kMergeBytes = 65536;           // ... + merged exponents (u8)
 constexpr uint32_t kLrBytes = kLrRows * 4;        // reward-free table: LEFT | RIGHT << 16 per row
