@@ -424,3 +424,40 @@ def test_cli_plays_the_reference_seed(r48, golden, capsys):
     assert capsys.readouterr().out.strip().endswith("score %d" % fp[0][1])
     assert main(["--episodes", "1000", "--seed", "3"]) == 0
     assert '"episodes": 1000' in capsys.readouterr().out
+
+
+def test_board_ids_wrap_mod_2_64(r48, orc):
+    """global ids are uint64 arithmetic: a batch that straddles 2^64 wraps the same way everywhere"""
+    base, n, seed = (1 << 64) - 7, 4001, 5
+    env = r48.BatchedGame(n, seed=seed, board_base=base)
+    b0 = orc.reset_batch(n, seed, base)
+    assert (to_u64(env.boards) == b0).all()
+    a = np.random.default_rng(8).integers(0, 4, n).astype(np.uint8)
+    boards, _, done = env.step(dev(a))
+    ob, _, od = orc.step_batch(b0, a, seed, base, 0)
+    assert (to_u64(boards) == ob).all() and (done.cpu().numpy() == od).all()
+    res = r48.random_rollouts(n, seed=seed, board_base=base)
+    fb, ln = orc.rollout(n, seed, base, threads=4)
+    assert (to_u64(res.final_boards) == fb).all() and (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
+
+
+def test_empty_and_tiny_batches(r48, orc):
+    """n = 0 is a no-op everywhere; n = 1 and 2 take the tail paths of the vector kernels"""
+    L = r48._native.lib()
+    assert L.r48_reset(None, 0, 0, 0, None) == 0
+    assert L.r48_step(None, None, None, None, None, 0, 0, 0, 0, 0, None, None) == 0
+    assert L.r48_afterstates(None, None, None, None, None, 0, 0, None) == 0
+    assert L.r48_rollout(0, 0, 0, None, None, None, None, None) == 0
+    for n in (1, 2, 3):
+        env = r48.BatchedGame(n, seed=1, board_base=9)
+        a = np.arange(n, dtype=np.uint8) % 4
+        b0 = to_u64(env.boards).copy()
+        boards, reward, done = env.step(dev(a))
+        ob, orw, od = orc.step_batch(b0, a, 1, 9, 0)
+        assert (to_u64(boards) == ob).all() and (done.cpu().numpy() == od).all()
+        after, _, valid, dn = r48.afterstates(env.boards)
+        oa, _, ov, odn = orc.afterstates_batch(to_u64(env.boards))
+        assert (to_u64(after) == oa).all() and (valid.cpu().numpy() == ov).all()
+        res = r48.random_rollouts(n, seed=2, board_base=3)
+        fb, ln = orc.rollout(n, 2, 3)
+        assert (to_u64(res.final_boards) == fb).all() and (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
