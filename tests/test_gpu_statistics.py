@@ -161,3 +161,15 @@ def test_afterstates_config4_properties(r48):
         assert bool((reward[:, a][~differs] == 0).all())
     assert bool(((valid == 0) == (done == 1)).all())
     assert 0 < int(done.sum()) < n
+
+
+def test_rollout_one_million_episodes_bit_exact(r48, orc):
+    """A larger differential run: 2^20 episodes (1.5e8 env-steps) on the GPU against the oracle
+    on all host threads -- every final board and every length."""
+    import os
+    n = 1 << 20
+    res = r48.random_rollouts(n, seed=0xDEADBEEF, board_base=1 << 40)
+    fb, ln = orc.rollout(n, 0xDEADBEEF, 1 << 40, threads=max(1, (os.cpu_count() or 4)))
+    assert (res.final_boards.cpu().numpy().view(np.uint64) == fb).all()
+    assert (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
+    assert (res.stats.cpu().numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
