@@ -483,6 +483,12 @@ def run_ours(args):
                          "ipc_per_sm_implied": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6),
                          "peak_formula": "148 SMs x 4 schedulers x sm_mhz (median under load) x 32 lanes / "
                                          "warp-instructions per 32 env-steps (ncu); frac = issue-slot utilisation",
+                         "measured_issue_ceiling_ipc_per_sm": 2.78,
+                         "frac_of_measured_ceiling": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6) / 2.78,
+                         "ceiling_note": "tools/ubench/pipes.cu: a synthetic 1:1 LOP3/IMAD stream (8 independent "
+                                         "chains per thread, 32 warps/SM) sustains 2.77-2.78 warp-instr/cycle/SM on "
+                                         "this chip, single-pipe integer streams 1.98 -- the nominal 4/cycle is not "
+                                         "reachable with integer work",
                          "traffic": prof.get("dram_bytes_per_launch"),
                          "traffic_note": "dram bytes of the profiled 2^22-episode launch (most of its 50 MB of "
                                          "outputs is still in L2 when the kernel ends)"})

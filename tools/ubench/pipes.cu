@@ -8,8 +8,8 @@
 #define ITERS 4096
 #define NCHAIN 8
 
-enum Op { LOP3, SHF_R, SHL_IMAD, PRMT, IADD3, IMAD, IMAD_HI, IMAD_WIDE, ISETP_SEL, POPC, LEA, VIMNMX, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_SHF_IMADSHL, LDS_NOCONF, LDS_RANDOM, IADD_IMAD, MIX_LOP_WIDE, NOPS };
-const char* names[] = {"LOP3","SHF.R","IMAD.SHL(mul 16)","PRMT","IADD3","IMAD","IMAD.HI.U32","IMAD.WIDE.U32","ISETP+SEL","POPC","LEA","VIMNMX","mix LOP3+IMAD 1:1","mix LOP3+IMAD.HI 1:1","mix SHF+IMAD.SHL 1:1","LDS no conflict","LDS random u16 idx","mad.lo x*1+y","mix LOP3+IMAD.WIDE 1:1"};
+enum Op { LOP3, SHF_R, SHL_IMAD, PRMT, IADD3, IMAD, IMAD_HI, IMAD_WIDE, ISETP_SEL, POPC, LEA, VIMNMX, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_SHF_IMADSHL, LDS_NOCONF, LDS_RANDOM, IADD_IMAD, MIX_LOP_WIDE, MIX_IMM, MIX3, MIX_2TO1, NOPS };
+const char* names[] = {"LOP3","SHF.R","IMAD.SHL(mul 16)","PRMT","IADD3","IMAD","IMAD.HI.U32","IMAD.WIDE.U32","ISETP+SEL","POPC","LEA","VIMNMX","mix LOP3+IMAD 1:1","mix LOP3+IMAD.HI 1:1","mix SHF+IMAD.SHL 1:1","LDS no conflict","LDS random u16 idx","mad.lo x*1+y","mix LOP3+IMAD.WIDE 1:1","mix LOP3(imm)+IMAD(imm) 1:1","mix LOP3+IMAD+PRMT+IMAD","mix LOP3:IMAD 2:1"};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long long* cycles)
@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long lon
 #pragma unroll
     for (int c = 0; c < NCHAIN; c++) x[c] = seed + threadIdx.x * 977u + c * 131u + blockIdx.x;
     uint32_t y = seed | 1u, z = seed * 3u + 7u;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
@@ -41,9 +42,12 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long lon
             if (OP == MIX_LOP_IMAD) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); }
             if (OP == MIX_LOP_IMADHI) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(y)); }
             if (OP == MIX_SHF_IMADSHL) { if (c & 1) asm volatile("shf.r.wrap.b32 %0, %0, %1, 5;" : "+r"(x[c]) : "r"(y)); else asm volatile("mul.lo.u32 %0, %0, 16;" : "+r"(x[c])); }
-            if (OP == LDS_NOCONF) { uint32_t a = (threadIdx.x & 31) * 4 + (x[c] & 0x7f80); asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[c]) : "r"(a)); }
-            if (OP == LDS_RANDOM) { uint32_t a = (x[c] & 0x7ffe); uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); x[c] = x[c] * 5u + v; }
+            if (OP == LDS_NOCONF) { uint32_t a = sbase + (threadIdx.x & 31) * 4 + (x[c] & 0x7f00); asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[c]) : "r"(a)); }
+            if (OP == LDS_RANDOM) { uint32_t a = sbase + (x[c] & 0x7ffe); uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); x[c] = x[c] * 5u + v; }
             if (OP == IADD_IMAD) asm volatile("mad.lo.u32 %0, %0, 1, %1;" : "+r"(x[c]) : "r"(y));
+            if (OP == MIX_IMM) { if (c & 1) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); }
+            if (OP == MIX3) { if ((c & 3) == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else if ((c & 3) == 2) asm volatile("prmt.b32 %0, %0, %1, 0x2301;" : "+r"(x[c]) : "r"(y)); else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); }
+            if (OP == MIX_2TO1) { if ((c % 3) != 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); }
             if (OP == MIX_LOP_WIDE) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else { uint64_t p; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x[c]), "r"(y)); x[c] = (uint32_t)(p >> 32) + (uint32_t)p; } }
         }
     }
@@ -80,6 +84,6 @@ int main()
     run<IADD3>(out, cyc, sms, 0); run<IMAD>(out, cyc, sms, 0); run<IMAD_HI>(out, cyc, sms, 0); run<IMAD_WIDE>(out, cyc, sms, 0);
     run<ISETP_SEL>(out, cyc, sms, 0); run<POPC>(out, cyc, sms, 0); run<LEA>(out, cyc, sms, 0); run<VIMNMX>(out, cyc, sms, 0);
     run<MIX_LOP_IMAD>(out, cyc, sms, 0); run<MIX_LOP_IMADHI>(out, cyc, sms, 0); run<MIX_SHF_IMADSHL>(out, cyc, sms, 0);
-    run<LDS_NOCONF>(out, cyc, sms, 0); run<LDS_RANDOM>(out, cyc, sms, 0); run<IADD_IMAD>(out, cyc, sms, 0); run<MIX_LOP_WIDE>(out, cyc, sms, 0);
+    run<LDS_NOCONF>(out, cyc, sms, 0); run<LDS_RANDOM>(out, cyc, sms, 0); run<IADD_IMAD>(out, cyc, sms, 0); run<MIX_LOP_WIDE>(out, cyc, sms, 0); run<MIX_IMM>(out, cyc, sms, 0); run<MIX3>(out, cyc, sms, 0); run<MIX_2TO1>(out, cyc, sms, 0);
     return 0;
 }
