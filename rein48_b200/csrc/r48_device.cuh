@@ -85,6 +85,51 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
 
+// The same function split for a caller that makes many calls with the same (c0, c1, c3 = 0) and a
+// varying c2 -- the rollout kernel: (id.lo, id.hi, tick >> 1, 0).  Round 0's M0*c0 product and
+// round 1's M1*c2 product then depend only on the episode, so they are computed once per episode.
+struct PhiloxEpisode {
+    uint32_t p0lo;      // lo(M0 * c0)                      -> c3 entering round 1
+    uint32_t q1lo;      // lo(M1 * (hi(M0*c0) ^ k1[0]))     -> c1 entering round 2
+    uint32_t q1hi;      // hi(M1 * (hi(M0*c0) ^ k1[0]))
+};
+
+__device__ __forceinline__ PhiloxEpisode philox_episode(uint32_t c0, const PhiloxKeys &K)
+{
+    const uint64_t p0 = (uint64_t)R48_PHILOX_M0 * c0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ K.k1[0];            // c3 = 0
+    const uint64_t q1 = (uint64_t)R48_PHILOX_M1 * n2;
+    return PhiloxEpisode{(uint32_t)p0, (uint32_t)q1, (uint32_t)(q1 >> 32)};
+}
+
+__device__ __forceinline__ void philox4x32_10_episode(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                       const PhiloxEpisode &E, const PhiloxKeys &K,
+                                                       uint32_t (&w)[4])
+{
+    // round 0 (M0*c0 and n2 come from E)
+    const uint64_t a1 = (uint64_t)R48_PHILOX_M1 * c2;
+    uint32_t x0 = (uint32_t)(a1 >> 32) ^ c1 ^ K.k0[0];             // c0 entering round 1
+    uint32_t x1 = (uint32_t)a1;                                    // c1 entering round 1
+    // round 1 (M1*c2 comes from E)
+    const uint64_t b0 = (uint64_t)R48_PHILOX_M0 * x0;
+    uint32_t y0 = E.q1hi ^ x1 ^ K.k0[1];
+    uint32_t y2 = (uint32_t)(b0 >> 32) ^ E.p0lo ^ K.k1[1];
+    uint32_t y1 = E.q1lo, y3 = (uint32_t)b0;
+    (void)c0;
+#pragma unroll
+    for (int r = 2; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)R48_PHILOX_M0 * y0;
+        const uint64_t p1 = (uint64_t)R48_PHILOX_M1 * y2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ y1 ^ K.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ y3 ^ K.k1[r];
+        y1 = (uint32_t)p1;
+        y3 = (uint32_t)p0;
+        y0 = n0;
+        y2 = n2;
+    }
+    w[0] = y0; w[1] = y1; w[2] = y2; w[3] = y3;
+}
+
 // Draw spec: tick t of board `id` uses call (id.lo, id.hi, t >> 1, 0) and the
 // word pair (2*(t&1), 2*(t&1)+1) = (a, v): action = a >> 30, cell = mulhi(a << 2, n_blank),
 // value = v < THRESHOLD ? 4 : 2.

@@ -483,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     // greedy policy: `failed` is simply set to 3 when no move changes the board
     uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
     uint32_t ep = kNone;
+    PhiloxEpisode pe = {0u, 0u, 0u};        // per-episode part of the Philox call
+    uint32_t id_lo = 0, id_hi = 0;
     uint32_t rec_len = 0;       // RECORD: length of the episode being replayed ...
     uint64_t rec_off = 0;       // ... and its first output slot
     bool live = true;           // the queue may still have work for this lane
@@ -504,6 +506,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 const uint32_t mine = base + __popc(want & ((1u << lane) - 1u));
                 if (mine < p.n) {
                     ep = mine; lo = 0; hi = 0; tick = 0; failed = 0;
+                    const uint64_t id = p.board_base + mine;
+                    id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
+                    pe = philox_episode(id_lo, p.keys);
                     if (RECORD) { rec_len = p.lengths[mine]; rec_off = p.traj_offsets[mine]; }
                 } else {                       // queue empty: park (failed stays 3, live off)
                     live = false; ep = kNone; rec_len = 0;
@@ -513,8 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         }
 
         uint32_t w[4];
-        const uint64_t id = p.board_base + ep;
-        philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), tick >> 1, 0u, p.keys, w);
+        philox4x32_10_episode(id_lo, id_hi, tick >> 1, pe, p.keys, w);
 
 #pragma unroll
         for (int half = 0; half < 2; half++) {
