@@ -117,7 +117,8 @@ int r48_spawn(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, u
 int r48_blank_counts(const uint64_t *boards, uint8_t *counts, int64_t n, void *stream);
 
 /* 1-ply afterstates: Game.update_matrix(copy, a) for a = 0..3 (GameClient.py:129-254), no
- * spawn.  out[4*i+a], reward[4*i+a]; valid[i] bit a = move a changes the board;
+ * spawn.  Planar outputs, one plane per action: out[a*n + i], reward[a*n + i] (so every store
+ * of a warp is one contiguous run); valid[i] bit a = move a changes the board;
  * done[i] = Game.has_game_over (GameClient.py:65-94).  reward/valid/done may be NULL. */
 int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid,
                     uint8_t *done, int64_t n, int reward_mode, void *stream);

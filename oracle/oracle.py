@@ -233,8 +233,8 @@ def env_step_batch(boards, actions, steps, episodes, seed, board_base, id_stride
 def afterstates_batch(boards, reward_mode=0):
     boards = np.ascontiguousarray(boards, np.uint64)
     n = boards.size
-    out = np.zeros((n, 4), np.uint64)
-    reward = np.zeros((n, 4), np.int32)
+    out = np.zeros((4, n), np.uint64)            # planar: one row per action
+    reward = np.zeros((4, n), np.int32)
     valid = np.zeros(n, np.uint8)
     done = np.zeros(n, np.uint8)
     lib().orc_afterstates_batch(boards, out.reshape(-1), reward.reshape(-1), valid, done, n,

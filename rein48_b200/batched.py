@@ -162,13 +162,14 @@ def _i64(boards):
 
 
 def afterstates(boards, reward_mode=0):
-    """-> (after [n,4] int64, reward [n,4] int32, valid [n] uint8 bitmask, done [n] uint8)"""
+    """-> (after [4,n] int64, reward [4,n] int32, valid [n] uint8 bitmask, done [n] uint8);
+    after[a] is the contiguous batch of boards after action a (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT)."""
     boards = _i64(boards)
     n = boards.numel()
     dev = boards.device
     with torch.cuda.device(dev):
-        out = torch.empty((n, 4), dtype=torch.int64, device=dev)
-        reward = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        out = torch.empty((4, n), dtype=torch.int64, device=dev)
+        reward = torch.empty((4, n), dtype=torch.int32, device=dev)
         valid = torch.empty(n, dtype=torch.uint8, device=dev)
         done = torch.empty(n, dtype=torch.uint8, device=dev)
         _native.check(_native.lib().r48_afterstates(

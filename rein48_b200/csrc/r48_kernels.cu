@@ -376,11 +376,12 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
 
 struct AfterParams {
     const uint64_t *in;
-    uint64_t *out;               // [n][4]
-    int32_t *reward;             // [n][4] or NULL
+    uint64_t *out;               // [4][plane] planar: out[a * plane + i]
+    int32_t *reward;             // [4][plane] or NULL
     uint8_t *valid;              // [n] or NULL
     uint8_t *done;               // [n] or NULL
-    int64_t n;
+    int64_t n;                   // boards of this launch
+    uint64_t plane;              // boards of the whole call = distance between action planes
     Tables tables;
 };
 
@@ -418,11 +419,12 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
                 res[a] = ((uint64_t)rh[a] << 32) | rl[a];
             }
         }
-        ulonglong2 *o = (ulonglong2 *)p.out + 2ull * i;
-        o[0] = make_ulonglong2(res[0], res[1]);
-        o[1] = make_ulonglong2(res[2], res[3]);
-        if (p.reward)
-            ((int4 *)p.reward)[i] = make_int4((int)rw[0], (int)rw[1], (int)rw[2], (int)rw[3]);
+#pragma unroll
+        for (uint32_t a = 0; a < 4; a++) p.out[a * p.plane + i] = res[a];     // 256 contiguous bytes per warp
+        if (p.reward) {
+#pragma unroll
+            for (uint32_t a = 0; a < 4; a++) p.reward[a * p.plane + i] = (int)rw[a];
+        }
         if (p.valid) p.valid[i] = (uint8_t)mask;
         // game over <=> no move changes a non-empty board (proof in DESIGN.md)
         if (p.done) p.done[i] = (uint8_t)(mask == 0u && b != 0ull);
@@ -1040,14 +1042,14 @@ int r48_afterstates(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t 
     if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_afterstates: reward_mode must be 0 or 1");
     if (n == 0) return R48_OK;
     if (!in || !out) return fail(R48_ERR_NULL, "r48_afterstates: in/out is NULL");
-    if (!aligned(in, 8) || !aligned(out, 16) || (reward && !aligned(reward, 16)))
-        return fail(R48_ERR_ALIGN, "r48_afterstates: in needs 8-byte, out/reward 16-byte alignment");
+    if (!aligned(in, 8) || !aligned(out, 8) || (reward && !aligned(reward, 4)))
+        return fail(R48_ERR_ALIGN, "r48_afterstates: misaligned pointer");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     for (int64_t off = 0; off < n; off += kChunk) {
         const int64_t m = n - off < kChunk ? n - off : kChunk;
-        AfterParams p{in + off, out + 4 * off, reward ? reward + 4 * off : nullptr, valid ? valid + off : nullptr,
-                      done ? done + off : nullptr, m, d->tables()};
+        AfterParams p{in + off, out + off, reward ? reward + off : nullptr, valid ? valid + off : nullptr,
+                      done ? done + off : nullptr, m, (uint64_t)n, d->tables()};
         const int grid = grid_for(m, kThreads, d->sms, 1);
         if (reward_mode)
             CK(launch_pdl(afterstates_kernel<true>, grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream, p));

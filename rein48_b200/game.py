@@ -105,7 +105,7 @@ class Game:
             after, _, valid, _ = B.afterstates(env.boards)
             k, vexp = 0, 0
             if (int(valid.item()) >> code) & 1:                          # has_changed
-                n_blank = int(B.blank_counts(after[0, code:code + 1]).item())
+                n_blank = int(B.blank_counts(after[code]).item())
                 k = random.randint(0, n_blank - 1)                       # GameClient.py:121
                 vexp = 1 if random.uniform(0, 1) > 0.1 else 2            # GameClient.py:125
             env.step_injected([code], [k], [vexp])
@@ -151,10 +151,10 @@ class Game:
         code = action_code(action)
         dev = _device(Game.default_device)
         after, reward, valid, _ = B.afterstates(_to_board(matrix, dev))
-        new = _to_matrix(after[0, code:code + 1])
+        new = _to_matrix(after[code])
         for i in range(4):
             matrix[i][:] = new[i]
-        return matrix, int(reward[0, code].item()), bool((int(valid.item()) >> code) & 1)
+        return matrix, int(reward[code, 0].item()), bool((int(valid.item()) >> code) & 1)
 
     @staticmethod
     def print_terminal(matrix):

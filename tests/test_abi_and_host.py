@@ -67,7 +67,7 @@ def test_argument_validation_needs_no_device(native):
     assert L.r48_reset(None, 0, 0, 0, None) == native.OK               # empty batch is a no-op
     assert L.r48_step(p, p, p, None, None, 4, 0, 0, 0, 2, None, None) == native.ERR_ARG
     assert L.r48_step(None, p, p, None, None, 4, 0, 0, 0, 0, None, None) == native.ERR_NULL
-    assert L.r48_afterstates(p, p + 8, None, None, None, 1, 0, None) == native.ERR_ALIGN
+    assert L.r48_afterstates(p, p + 4, None, None, None, 1, 0, None) == native.ERR_ALIGN
     assert L.r48_rollout(4, 0, 0, p, None, None, p, None) == native.ERR_NULL
     assert L.r48_rollout(0, 0, 0, None, None, None, None, None) == native.OK
     assert b"NULL" in L.r48_last_error()

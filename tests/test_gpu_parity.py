@@ -66,7 +66,7 @@ def test_row_tables_exhaustive(r48, orc, golden):
 def test_afterstates_golden_boards(r48, golden):
     g = golden("boards_ref.npz")
     after, reward, valid, done = r48.afterstates(boards_to_dev(g["boards"]))
-    assert (to_u64(after) == g["after"]).all()
+    assert (to_u64(after).T == g["after"]).all()
     changed = (valid.cpu().numpy()[:, None] >> np.arange(4)) & 1
     assert (changed == g["changed"]).all()
     assert (done.cpu().numpy() == g["over"]).all()
@@ -109,7 +109,7 @@ def test_step_injected_vs_oracle_ragged(r48, orc):
         # k must be < n_blank of the moved board for the oracle; reduce modulo that count
         moved, _, _, _ = orc.afterstates_batch(b)
         blanks = np.array([sum(((int(m) >> (4 * p)) & 15) == 0 for p in range(16))
-                           for m in moved[np.arange(n + off), a]])
+                           for m in moved[a, np.arange(n + off)]])
         k = np.where(blanks > 0, k % np.maximum(blanks, 1), 0).astype(np.uint8)
         L = r48._native.lib()
         d_in, d_a, d_k, d_v = boards_to_dev(b), dev(a), dev(k), dev(v)
@@ -332,8 +332,8 @@ def test_step_host_entry(r48, orc, n):
 def test_afterstates_host_entry(r48, orc):
     n = 33333
     b = random_boards(n, 78)
-    out = np.zeros((n, 4), np.uint64)
-    rw = np.zeros((n, 4), np.int32)
+    out = np.zeros((4, n), np.uint64)
+    rw = np.zeros((4, n), np.int32)
     va = np.zeros(n, np.uint8)
     dn = np.zeros(n, np.uint8)
     L = r48._native.lib()

@@ -136,7 +136,7 @@ def test_step_config2_properties(r48):
         assert bool(((gain == 2) | (gain == 4))[changed].all())
         assert bool((new == boards)[~changed].all())
         assert bool((reward == 0).all())
-        moved = after_all.gather(1, acts.to(torch.int64)[:, None])[:, 0]
+        moved = after_all.gather(0, acts.to(torch.int64)[None, :])[0]
         assert bool(((new ^ moved) != 0)[changed].all()) and bool((r48.blank_counts(moved)[changed] >= 1).all())
         _, _, v2, d2 = r48.afterstates(new)
         assert bool((done == d2).all())
@@ -153,12 +153,12 @@ def test_afterstates_config4_properties(r48):
     after, reward, valid, done = r48.afterstates(boards, reward_mode=1)
     base, _ = r48.scores(boards)
     for a in range(4):
-        col = after[:, a].contiguous()
+        col = after[a]
         sc, _ = r48.scores(col)
         assert bool((sc == base).all())
         differs = col != boards
         assert bool((differs == ((valid >> a) & 1).bool()).all())
-        assert bool((reward[:, a][~differs] == 0).all())
+        assert bool((reward[a][~differs] == 0).all())
     assert bool(((valid == 0) == (done == 1)).all())
     assert 0 < int(done.sum()) < n
 

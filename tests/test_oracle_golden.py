@@ -102,7 +102,7 @@ def test_boards_against_reference(orc, golden):
     g = golden("boards_ref.npz")
     boards = g["boards"]
     out, _, valid, done = orc.afterstates_batch(boards)
-    assert (out == g["after"]).all()
+    assert (out.T == g["after"]).all()
     got_changed = (valid[:, None] >> np.arange(4)) & 1
     assert (got_changed == g["changed"]).all()
     assert (done == g["over"]).all()
