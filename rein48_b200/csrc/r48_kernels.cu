@@ -327,44 +327,59 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     bool ready = false;
     uint32_t bad = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        const uint64_t b = p.boards[i];
-        const uint32_t a = p.action[i];
-        uint32_t st = p.steps[i], ep = p.episodes[i];
-        uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
-        uint32_t aw, vw;
-        draw_words(id, st + 1u, p.keys, aw, vw);
-        if (!ready) { mbar_wait(&bar, 0); ready = true; }
-        uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d;
-        int32_t r;
-        step_one<REWARD, false>(lo, hi, a, aw, vw, smem, lr, r, d, bad);
-        st += 1u;
-        if (d && p.auto_reset) {                 // rare: a lane's game ended
-            if (p.final_boards) p.final_boards[i] = ((uint64_t)hi << 32) | lo;
-            ep += 1u; st = 0u;
-            id = p.board_base + i + (uint64_t)ep * p.id_stride;
-            draw_words(id, 0u, p.keys, aw, vw);
-            lo = 0u; hi = 0u;
-            const Blanks bl = count_blanks(lo, hi);
-            place_tile(lo, hi, bl, __umulhi(aw << 2, bl.n), vw < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+    const uint32_t lane = threadIdx.x & 31u;
+    // warp-uniform trip count: the readout below shuffles boards between the lanes of a warp
+    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < p.n; base += stride) {
+        const uint32_t i = base + lane;
+        const bool act = i < p.n;
+        uint32_t lo = 0u, hi = 0u;
+        if (act) {
+            const uint64_t b = p.boards[i];
+            const uint32_t a = p.action[i];
+            uint32_t st = p.steps[i], ep = p.episodes[i];
+            uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
+            uint32_t aw, vw;
+            draw_words(id, st + 1u, p.keys, aw, vw);
+            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            lo = (uint32_t)b; hi = (uint32_t)(b >> 32);
+            uint32_t d;
+            int32_t r;
+            step_one<REWARD, false>(lo, hi, a, aw, vw, smem, lr, r, d, bad);
+            st += 1u;
+            if (d && p.auto_reset) {                 // rare: a lane's game ended
+                if (p.final_boards) p.final_boards[i] = ((uint64_t)hi << 32) | lo;
+                ep += 1u; st = 0u;
+                id = p.board_base + i + (uint64_t)ep * p.id_stride;
+                draw_words(id, 0u, p.keys, aw, vw);
+                lo = 0u; hi = 0u;
+                const Blanks bl = count_blanks(lo, hi);
+                place_tile(lo, hi, bl, __umulhi(aw << 2, bl.n), vw < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+            }
+            p.boards[i] = ((uint64_t)hi << 32) | lo;
+            p.steps[i] = st;
+            p.episodes[i] = ep;
+            if (p.reward) p.reward[i] = r;
+            if (p.done) p.done[i] = (uint8_t)d;
         }
-        p.boards[i] = ((uint64_t)hi << 32) | lo;
-        p.steps[i] = st;
-        p.episodes[i] = ep;
-        if (p.reward) p.reward[i] = r;
-        if (p.done) p.done[i] = (uint8_t)d;
         if (p.obs) {
-            float4 *o = (float4 *)p.obs + 4ull * i;
+            // Readout of the warp's 32 boards (2 KB of float32) as four 512-byte contiguous runs:
+            // in run k lane L writes row L%4 of board 8k + L/4, fetched from the owning lane by
+            // shuffle.  (Each lane writing its own board's 64 bytes half-fills every sector it
+            // touches and stalls the store queue -- see afterstates in DESIGN.md.)
+            const uint32_t row = lane & 3u;
 #pragma unroll
-            for (int row = 0; row < 4; row++) {
-                const uint32_t w = (row < 2 ? lo : hi) >> (16 * (row & 1));
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t src = 8u * k + (lane >> 2);
+                const uint32_t slo = __shfl_sync(kFull, lo, src), shi = __shfl_sync(kFull, hi, src);
+                const uint32_t w = ((row & 2u) ? shi : slo) >> (16u * (row & 1u));
                 float v[4];
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     const uint32_t e = (w >> (4 * t)) & 15u;
                     v[t] = p.obs_log2 ? (float)e : (float)((1u << e) & ~1u);
                 }
-                o[row] = make_float4(v[0], v[1], v[2], v[3]);
+                const uint32_t tb = base + src;
+                if (tb < p.n) ((float4 *)p.obs)[4ull * tb + row] = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
     }
