@@ -537,8 +537,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         mst = e0.elapsed_time(e1)
         line["trajectories"] = {"workload": "2^22 random episodes, all transitions kept (9 B per step)",
-                                "transitions": tr.boards.numel(), "ms": mst,
-                                "transitions_per_sec": tr.boards.numel() / (mst * 1e-3),
+                                "transitions": tr.transitions, "ms": mst,
+                                "transitions_per_sec": tr.transitions / (mst * 1e-3),
                                 "GBps_written": 9 * tr.boards.numel() / (mst * 1e-3) / 1e9}
         tr = None
         torch.cuda.empty_cache()

@@ -149,8 +149,11 @@ int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy
  * function of (seed, id) -- and writes, for step t = 1..lengths[i] of episode i,
  *     traj_boards[offsets[i] + t-1]  = the board BEFORE the step (the state the policy saw)
  *     traj_actions[offsets[i] + t-1] = the action taken
- * lengths[] comes from r48_rollout(_policy) with the same arguments, offsets[] is its exclusive
- * prefix sum; the board after the last step is final_boards[i] of that call. */
+ * lengths[] comes from r48_rollout(_policy) with the same arguments.  offsets[i] must be a
+ * MULTIPLE OF 4 with room for lengths[i] rounded up to a multiple of 4 (e.g. the exclusive prefix
+ * sum of (lengths + 3) & ~3): four steps leave as one 32-byte sector, and the up-to-3 padding
+ * slots after an episode's last step hold unspecified values.  traj_boards must be 32-byte,
+ * traj_actions 4-byte aligned.  The board after the last step is final_boards[i] of that call. */
 int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int policy,
                              const uint32_t *lengths, const uint64_t *offsets, uint64_t *traj_boards,
                              uint8_t *traj_actions, void *workspace, void *stream);

@@ -503,7 +503,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     PhiloxEpisode pe = {0u, 0u, 0u};        // per-episode part of the Philox call
     uint32_t id_lo = 0, id_hi = 0;
     uint32_t rec_len = 0;       // RECORD: length of the episode being replayed ...
-    uint64_t rec_off = 0;       // ... and its first output slot
+    uint64_t rec_off = 0;       // ... and its first output slot (a multiple of 4)
+    // RECORD: four steps are gathered in registers and leave as one full 32-byte sector (two
+    // 128-bit stores) + one 32-bit store of the four actions.  One store of 8 bytes per lane per
+    // tick, every lane in a different sector, made the replay pass LSU-bound (3x the play pass).
+    uint32_t tb_lo[4] = {0u, 0u, 0u, 0u}, tb_hi[4] = {0u, 0u, 0u, 0u}, tact = 0u;
     bool live = true;           // the queue may still have work for this lane
     mbar_wait(&bar, 0);
 
@@ -538,7 +542,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         philox4x32_10_episode(id_lo, id_hi, tick >> 1, pe, p.keys, w);
 
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
+        for (int half_i = 0; half_i < 2; half_i++) {
+            const int half = half_i;
             const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
             const uint32_t olo = lo, ohi = hi;
             uint32_t taken = aw >> 30;
@@ -565,9 +570,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
                 lo = bl; hi = bh;
             }
-            if (RECORD && tick - 1u < rec_len) {         // steps 1..length of a live episode
-                p.traj_boards[rec_off + (tick - 1u)] = ((uint64_t)ohi << 32) | olo;
-                p.traj_actions[rec_off + (tick - 1u)] = (uint8_t)taken;
+            if (RECORD) {
+                // Ticks enter the loop in pairs starting at an even tick, so slot s = tick - 1 is
+                // odd in the first half and even in the second: j = s & 3 is {1,3} / {0,2}.
+                const uint32_t s = tick - 1u;
+                const bool rec = s < rec_len;                // steps 1..length of a live episode
+                const bool upper = (s & 2u) != 0u;
+                const int jl = 1 - half, ju = 3 - half;      // half 0: j in {1,3}; half 1: {0,2} (static after unrolling)
+                if (rec && !upper) { tb_lo[jl] = olo; tb_hi[jl] = ohi; }
+                if (rec && upper) { tb_lo[ju] = olo; tb_hi[ju] = ohi; }
+                if (rec) tact = __byte_perm(tact, taken, upper ? (ju == 3 ? 0x4210 : 0x3410) : (jl == 1 ? 0x3240 : 0x3214));
+                const bool flush = rec && ((s & 3u) == 3u || s + 1u == rec_len);
+                if (flush) {
+                    const uint64_t g = rec_off + (s & ~3u);
+                    uint4 *dst = (uint4 *)(p.traj_boards + g);
+                    dst[0] = make_uint4(tb_lo[0], tb_hi[0], tb_lo[1], tb_hi[1]);
+                    dst[1] = make_uint4(tb_lo[2], tb_hi[2], tb_lo[3], tb_hi[3]);
+                    *(uint32_t *)(p.traj_actions + g) = tact;
+                }
             }
             const Blanks b = count_blanks(lo, hi);
             const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
@@ -1134,8 +1154,9 @@ int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int 
     if (n == 0) return R48_OK;
     if (!lengths || !offsets || !traj_boards || !traj_actions || !workspace)
         return fail(R48_ERR_NULL, "r48_rollout_trajectories: NULL pointer");
-    if (!aligned(lengths, 4) || !aligned(offsets, 8) || !aligned(traj_boards, 8) || !aligned(workspace, 8))
-        return fail(R48_ERR_ALIGN, "r48_rollout_trajectories: misaligned pointer");
+    if (!aligned(lengths, 4) || !aligned(offsets, 8) || !aligned(traj_boards, 32) || !aligned(traj_actions, 4) ||
+        !aligned(workspace, 8))
+        return fail(R48_ERR_ALIGN, "r48_rollout_trajectories: traj_boards needs 32-byte, traj_actions 4-byte alignment");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     cudaStream_t s = (cudaStream_t)stream;

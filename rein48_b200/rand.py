@@ -68,21 +68,35 @@ def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_s
     return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats)
 
 
-Trajectories = namedtuple("Trajectories", "offsets boards actions final_boards lengths stats")
+class Trajectories(namedtuple("Trajectories", "offsets boards actions final_boards lengths stats")):
+    """Flat (state, action) log of a batch of episodes; see rollout_trajectories."""
+
+    def valid_mask(self):
+        """bool[T]: True on slots that hold a step (False on the alignment padding)."""
+        t = self.boards.numel()
+        slot = torch.arange(t, device=self.boards.device)
+        ep = torch.searchsorted(self.offsets[1:].contiguous(), slot, right=True)
+        return slot - self.offsets[ep] < self.lengths.to(torch.int64)[ep]
+
+    @property
+    def transitions(self):
+        return int(self.lengths.sum().item())
 
 
 def rollout_trajectories(n, seed=0, device="cuda", board_base=0, policy="random"):
     """Play n episodes and keep every transition: data generation for the learners (the
     reference's README: "run tens of thousands of games on the GPU to make data").
     Returns Trajectories(offsets int64[n+1], boards int64[T], actions uint8[T], final_boards,
-    lengths, stats) with T = total steps; steps of episode i are offsets[i]..offsets[i+1]-1,
-    boards[] holds the state BEFORE each step, the state after the last one is final_boards[i]."""
+    lengths, stats).  Episode i occupies slots offsets[i] .. offsets[i] + lengths[i] - 1 (every
+    episode starts on a multiple of 4 slots; the up-to-3 slots of padding behind it are
+    unspecified); boards[] holds the state BEFORE each step, the state after the last one is
+    final_boards[i].  `valid_mask()` on the result marks the real slots."""
     res = random_rollouts(n, seed=seed, device=device, board_base=board_base, policy=policy)
     dev = res.final_boards.device
     L = _native.lib()
     with torch.cuda.device(dev):
         offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(res.lengths, 0, out=offsets[1:])
+        torch.cumsum((res.lengths.to(torch.int64) + 3) & ~3, 0, out=offsets[1:])
         total = int(offsets[-1].item())
         boards = torch.empty(total, dtype=torch.int64, device=dev)
         actions = torch.empty(total, dtype=torch.uint8, device=dev)

@@ -243,17 +243,20 @@ def test_rollout_trajectories_vs_oracle(r48, orc, policy, code):
     n = 3000
     tr = r48.rollout_trajectories(n, seed=SEED, board_base=BIG_BASE, policy=policy)
     off, boards, actions, final = orc.rollout_trajectories(n, SEED, BIG_BASE, code)
-    assert (tr.offsets.cpu().numpy() == off).all()
-    assert (to_u64(tr.boards) == boards).all()
-    assert (tr.actions.cpu().numpy() == actions).all()
+    assert (tr.offsets.cpu().numpy() == off).all() and (off % 4 == 0).all()
+    valid = tr.valid_mask()
+    v = valid.cpu().numpy()
+    assert int(v.sum()) == tr.transitions == int(tr.lengths.sum())
+    assert (to_u64(tr.boards)[v] == boards[v]).all()
+    assert (tr.actions.cpu().numpy()[v] == actions[v]).all()
     assert (to_u64(tr.final_boards) == final).all()
     # consistency on the GPU alone: stepping the recorded state with the recorded action gives
     # the next recorded state up to the spawned tile (same tile mass + 2 or 4)
-    sc, _ = r48.scores(tr.boards)
-    nxt = torch.cat([tr.boards[1:], tr.final_boards[-1:]])
-    last = torch.zeros_like(tr.boards, dtype=torch.bool)
-    last[tr.offsets[1:] - 1] = True
-    nxt[last] = tr.final_boards
+    b = tr.boards[valid]
+    sc, _ = r48.scores(b)
+    ends = torch.cumsum(tr.lengths.to(torch.int64), 0) - 1          # last step of each episode (compacted index)
+    nxt = torch.cat([b[1:], b[:1]])
+    nxt[ends] = tr.final_boards
     sn, _ = r48.scores(nxt)
     gain = sn - sc
     assert bool(((gain == 0) | (gain == 2) | (gain == 4)).all())
