@@ -232,6 +232,9 @@ __device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool towa
     return o | (o << 16);
 }
 
+// GUARD = false skips the range test: only for callers that can PROVE every row is in the table
+// (the rollout kernel: a board whose tiles sum to less than 16384 has no 16384 tile).
+template <bool GUARD = true>
 __device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t lr)
 {
     const bool vertical = action < 2u;
@@ -239,7 +242,7 @@ __device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t act
     if (vertical) transpose(lo, hi);
     const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
     uint32_t o0, o1, o2, o3;
-    if (__builtin_expect((r0 | r1 | r2 | r3) < kLrRows, 1)) {   // OR >= any row: conservative
+    if (!GUARD || __builtin_expect((r0 | r1 | r2 | r3) < kLrRows, 1)) {   // OR >= any row: conservative
         o0 = lds_u32(lr + 4u * r0); o1 = lds_u32(lr + 4u * r1);
         o2 = lds_u32(lr + 4u * r2); o3 = lds_u32(lr + 4u * r3);
     } else {

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/r48.h"
 #include "r48_device.cuh"
@@ -531,8 +532,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                     id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
                     pe = philox_episode(id_lo, p.keys);
                     if (RECORD) { rec_len = p.lengths[mine]; rec_off = p.traj_offsets[mine]; }
-                } else {                       // queue empty: park (failed stays 3, live off)
+                } else {                       // queue empty: park on the empty board (failed stays 3)
                     live = false; ep = kNone; rec_len = 0;
+                    lo = 0; hi = 0; tick = 2;
                 }
             }
             if (!__any_sync(kFull, live)) break;
@@ -541,65 +543,76 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         uint32_t w[4];
         philox4x32_10_episode(id_lo, id_hi, tick >> 1, pe, p.keys, w);
 
+        // The tiles of a board sum to at most 4 per spawn, so before tick 4000 no tile can be
+        // 16384 and every row is inside the LR table: the range test of move_lr is provably
+        // dead.  One warp vote per pair of ticks selects the unguarded body (always, in
+        // practice: random games last a few hundred ticks); the guarded one stays for the rest.
+        auto two_ticks = [&](auto guard_tag) {
+            constexpr bool kGuard = decltype(guard_tag)::value;
 #pragma unroll
-        for (int half_i = 0; half_i < 2; half_i++) {
-            const int half = half_i;
-            const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
-            const uint32_t olo = lo, ohi = hi;
-            uint32_t taken = aw >> 30;
-            bool changed;
-            if (POLICY == kPolicyRandom) {
-                move_lr(lo, hi, aw >> 30, lr);
-                // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
-                changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
-            } else {
-                // all four afterstates; key = blanks * 4 + (3 - rotation offset), -1 if the move
-                // changes nothing: the maximum is the greedy choice with the first-best tie rule
-                uint32_t rl[4], rh[4];
-                move_all(lo, hi, lr, rl, rh);
-                const uint32_t r = aw >> 30;
-                int best = -1;
-                uint32_t bl = lo, bh = hi;
+            for (int half_i = 0; half_i < 2; half_i++) {
+                const int half = half_i;
+                const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
+                const uint32_t olo = lo, ohi = hi;
+                uint32_t taken = aw >> 30;
+                bool changed;
+                if (POLICY == kPolicyRandom) {
+                    move_lr<kGuard>(lo, hi, aw >> 30, lr);
+                    // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
+                    changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
+                } else {
+                    // all four afterstates; key = blanks * 4 + (3 - rotation offset), -1 if the move
+                    // changes nothing: the maximum is the greedy choice with the first-best tie rule
+                    uint32_t rl[4], rh[4];
+                    move_all(lo, hi, lr, rl, rh);
+                    const uint32_t r = aw >> 30;
+                    int best = -1;
+                    uint32_t bl = lo, bh = hi;
 #pragma unroll
-                for (uint32_t a = 0; a < 4; a++) {
-                    const bool valid = ((rl[a] ^ lo) | (rh[a] ^ hi)) != 0u;
-                    const int key = valid ? (int)(blank_count(rl[a], rh[a]) * 4u + (3u - ((a - r) & 3u))) : -1;
-                    if (key > best) { best = key; bl = rl[a]; bh = rh[a]; taken = a; }
+                    for (uint32_t a = 0; a < 4; a++) {
+                        const bool valid = ((rl[a] ^ lo) | (rh[a] ^ hi)) != 0u;
+                        const int key = valid ? (int)(blank_count(rl[a], rh[a]) * 4u + (3u - ((a - r) & 3u))) : -1;
+                        if (key > best) { best = key; bl = rl[a]; bh = rh[a]; taken = a; }
+                    }
+                    changed = best >= 0 || tick == 0u;
+                    if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
+                    lo = bl; hi = bh;
                 }
-                changed = best >= 0 || tick == 0u;
-                if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
-                lo = bl; hi = bh;
-            }
-            if (RECORD) {
-                // Ticks enter the loop in pairs starting at an even tick, so slot s = tick - 1 is
-                // odd in the first half and even in the second: j = s & 3 is {1,3} / {0,2}.
-                const uint32_t s = tick - 1u;
-                const bool rec = s < rec_len;                // steps 1..length of a live episode
-                const bool upper = (s & 2u) != 0u;
-                const int jl = 1 - half, ju = 3 - half;      // half 0: j in {1,3}; half 1: {0,2} (static after unrolling)
-                if (rec && !upper) { tb_lo[jl] = olo; tb_hi[jl] = ohi; }
-                if (rec && upper) { tb_lo[ju] = olo; tb_hi[ju] = ohi; }
-                if (rec) tact = __byte_perm(tact, taken, upper ? (ju == 3 ? 0x4210 : 0x3410) : (jl == 1 ? 0x3240 : 0x3214));
-                const bool flush = rec && ((s & 3u) == 3u || s + 1u == rec_len);
-                if (flush) {
-                    const uint64_t g = rec_off + (s & ~3u);
-                    uint4 *dst = (uint4 *)(p.traj_boards + g);
-                    dst[0] = make_uint4(tb_lo[0], tb_hi[0], tb_lo[1], tb_hi[1]);
-                    dst[1] = make_uint4(tb_lo[2], tb_hi[2], tb_lo[3], tb_hi[3]);
-                    *(uint32_t *)(p.traj_actions + g) = tact;
+                if (RECORD) {
+                    // Ticks enter the loop in pairs starting at an even tick, so slot s = tick - 1 is
+                    // odd in the first half and even in the second: j = s & 3 is {1,3} / {0,2}.
+                    const uint32_t s = tick - 1u;
+                    const bool rec = s < rec_len;                // steps 1..length of a live episode
+                    const bool upper = (s & 2u) != 0u;
+                    const int jl = 1 - half, ju = 3 - half;      // static after unrolling
+                    if (rec && !upper) { tb_lo[jl] = olo; tb_hi[jl] = ohi; }
+                    if (rec && upper) { tb_lo[ju] = olo; tb_hi[ju] = ohi; }
+                    if (rec) tact = __byte_perm(tact, taken, upper ? (ju == 3 ? 0x4210 : 0x3410) : (jl == 1 ? 0x3240 : 0x3214));
+                    const bool flush = rec && ((s & 3u) == 3u || s + 1u == rec_len);
+                    if (flush) {
+                        const uint64_t g = rec_off + (s & ~3u);
+                        uint4 *dst = (uint4 *)(p.traj_boards + g);
+                        dst[0] = make_uint4(tb_lo[0], tb_hi[0], tb_lo[1], tb_hi[1]);
+                        dst[1] = make_uint4(tb_lo[2], tb_hi[2], tb_lo[3], tb_hi[3]);
+                        *(uint32_t *)(p.traj_actions + g) = tact;
+                    }
                 }
+                const Blanks b = count_blanks(lo, hi);
+                const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
+                place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), v29);
+                if (POLICY == kPolicyRandom) {
+                    // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
+                    const uint32_t axis = 2u - (aw >> 31);
+                    failed = changed ? 0u : (b.n == 0u ? (failed | axis) : failed);
+                    last_change = changed ? tick : last_change;
+                }
+                tick++;
             }
-            const Blanks b = count_blanks(lo, hi);
-            const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
-            place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), v29);
-            if (POLICY == kPolicyRandom) {
-                // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
-                const uint32_t axis = 2u - (aw >> 31);
-                failed = changed ? 0u : (b.n == 0u ? (failed | axis) : failed);
-                last_change = changed ? tick : last_change;
-            }
-            tick++;
-        }
+        };
+        constexpr bool kCanElide = POLICY == kPolicyRandom && !RECORD;
+        // parked lanes (live == false) sit on the empty board
+        if (kCanElide && __all_sync(kFull, tick < 4000u || !live)) two_ticks(std::false_type{});
+        else two_ticks(std::true_type{});
     }
 }
 
