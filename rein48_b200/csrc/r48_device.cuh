@@ -256,6 +256,7 @@ __device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t act
 }
 
 // all four afterstates: LEFT/RIGHT share one lookup per row, UP/DOWN one per column
+template <bool GUARD = true>
 __device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, uint32_t lr,
                                          uint32_t (&rl)[4], uint32_t (&rh)[4])
 {
@@ -267,7 +268,7 @@ __device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, uint32_t lr,
     uint32_t any = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) any |= r[t];
-    if (__builtin_expect(any < kLrRows, 1)) {
+    if (!GUARD || __builtin_expect(any < kLrRows, 1)) {
 #pragma unroll
         for (int t = 0; t < 8; t++) o[t] = lds_u32(lr + 4u * r[t]);
     } else {

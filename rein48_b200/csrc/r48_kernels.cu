@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                     // all four afterstates; key = blanks * 4 + (3 - rotation offset), -1 if the move
                     // changes nothing: the maximum is the greedy choice with the first-best tie rule
                     uint32_t rl[4], rh[4];
-                    move_all(lo, hi, lr, rl, rh);
+                    move_all<kGuard>(lo, hi, lr, rl, rh);
                     const uint32_t r = aw >> 30;
                     int best = -1;
                     uint32_t bl = lo, bh = hi;
@@ -609,9 +609,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 tick++;
             }
         };
-        constexpr bool kCanElide = POLICY == kPolicyRandom && !RECORD;
         // parked lanes (live == false) sit on the empty board
-        if (kCanElide && __all_sync(kFull, tick < 4000u || !live)) two_ticks(std::false_type{});
+        if (__all_sync(kFull, tick < 4000u || !live)) two_ticks(std::false_type{});
         else two_ticks(std::true_type{});
     }
 }
