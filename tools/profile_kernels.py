@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: launches each hot kernel a few times at a fixed size.
 
-    python tools/profile_kernels.py [rollout|step|afterstates|all] [--rollout-log2 22]
+    python tools/profile_kernels.py [rollout|step|afterstates|env|greedy|traj|all] [--rollout-log2 22]
 """
 import argparse
 import os
@@ -55,6 +55,26 @@ def main():
             r48.afterstates(boards)
         torch.cuda.synchronize()
         print("afterstates done")
+    if a.which in ("env", "all"):
+        m = 1 << 20
+        env = r48.BatchedGame(m, seed=7)
+        act = torch.randint(0, 4, (m,), device="cuda", dtype=torch.uint8)
+        for i in range(a.reps + 40):
+            env.env_step(act)
+        torch.cuda.synchronize()
+        print("env_step done")
+    if a.which in ("greedy", "all"):
+        n = 1 << a.rollout_log2
+        buf = r48.RolloutBuffers(n)
+        for i in range(a.reps):
+            r48.random_rollouts(n, seed=2048 + i, buffers=buf, policy="greedy_blanks")
+        torch.cuda.synchronize()
+        print("greedy", r48.EpisodeStats(buf.stats).summary())
+    if a.which in ("traj", "all"):
+        for i in range(a.reps):
+            tr = r48.rollout_trajectories(1 << 20, seed=2048 + i)
+        torch.cuda.synchronize()
+        print("trajectories", tr.transitions)
 
 
 if __name__ == "__main__":
