@@ -1357,10 +1357,17 @@ int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *fi
     if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
     // Large batches go in chunks of 2^23 episodes: the per-episode results of chunk i travel to
     // the host on the copy stream while chunk i+1 is being played.
-    const int64_t chunk = n > ((int64_t)1 << 24) ? ((int64_t)1 << 23) : n;
+    // The copy of the LAST chunk is the only one left exposed, so the chunks shrink toward the end
+    // (..., 2^23, 2^22, 2^21, 2^20, 2^20): small chunks run a little less efficiently but hide
+    // most of that tail.
+    const int64_t big = (int64_t)1 << 23, small = (int64_t)1 << 20;
     int slot = 0;
-    for (int64_t off = 0; off < n; off += chunk, slot ^= 1) {
-        const int64_t m = n - off < chunk ? n - off : chunk;
+    for (int64_t off = 0, m = 0; off < n; off += m, slot ^= 1) {
+        const int64_t left = n - off;
+        if (n <= ((int64_t)1 << 24)) m = left;                 // small batches: one launch
+        else if (left > 2 * big) m = big;
+        else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
+        else m = left;
         rc = r48_rollout(m, seed, board_base + (uint64_t)off, d_fb + off, d_len + off,
                          stats ? d_stats : nullptr, d->arena + o_ws, s);
         if (rc) return rc;
