@@ -20,7 +20,6 @@ import random
 
 import torch
 
-from . import _native
 from . import batched as B
 
 _ACTIONS = (

@@ -3,7 +3,6 @@
 reference: every fixture under tests/golden/ was produced by running the unmodified
 reference (tests/golden/make_golden.py).  CPU only."""
 import os
-import random
 
 import numpy as np
 import pytest
