@@ -1117,7 +1117,7 @@ int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int
         return fail(R48_ERR_ALIGN, "r48_episode_stats: misaligned pointer");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
-    stats_kernel<<<grid_for(n, 256, d->sms, 4), 256, 0, (cudaStream_t)stream>>>(
+    stats_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(
         final_boards, lengths, n, (unsigned long long *)stats);
     CK(cudaGetLastError());
     return R48_OK;
