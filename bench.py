@@ -184,6 +184,24 @@ def rollout_issue_profile():
     return None
 
 
+def ncu_traffic(profile, index=0):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from a committed ncu summary
+    (profiles/*.json, one `ncu --set full` capture per kernel); None if the file is missing."""
+    path = os.path.join(ROOT, "profiles", profile)
+    try:
+        d = json.load(open(path))[index]
+    except (OSError, IndexError, ValueError):
+        return None
+    total = 0.0
+    for key, val in d.items():
+        if key.startswith("dram__bytes_read.sum") or key.startswith("dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(key.split("[")[-1].rstrip("]"), None)
+            if scale is None:
+                return None
+            total += float(val) * scale
+    return total
+
+
 def time_launches(torch, fn, iters):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -251,7 +269,10 @@ def bench_step_kernel(torch, r48, hbm_peak):
                        "64 launches captured in a CUDA graph, timed with CUDA events over 10 replays",
            "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                        "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+                        "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_step_ncu.json", 0),
+                        "traffic_note": "ncu, one 2^20-board launch: the 9.7 MB read is the input; the 13.6 MB of "
+                                        "outputs is still in L2 when the kernel ends (8M-board launch: 136 MB of "
+                                        "176 MB algorithmic)"}}
     # the same kernel on one 16M-board launch (352 MB): launch latency amortised
     nbig = n * sets
     def launch_big(i):
@@ -311,7 +332,7 @@ def bench_env_step_kernel(torch, r48, hbm_peak):
                         "readout, 8 rotating env sets",
             "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_env_ncu.json", 0)}}
 
 
 def bench_afterstates_kernel(torch, r48, hbm_peak):
@@ -336,7 +357,7 @@ def bench_afterstates_kernel(torch, r48, hbm_peak):
     return {"workload": "config 4: 2^23 boards x 4 afterstates + valid mask + done, 464 MB per launch (> L2)",
             "us_per_launch": ms * 1e3, "boards_per_sec": n / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None}}
+                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_afterstates_ncu.json", 0)}}
 
 
 def run_ours(args):
