@@ -67,6 +67,8 @@ class BatchedGame:
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.steps = 0
+        # the four state tensors live as long as the object: their addresses are fetched once
+        self._ptrs = (self.boards.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr())
         self.reset()
 
     # -- Game.reset (GameClient.py:33-38): one tile per board
@@ -83,14 +85,21 @@ class BatchedGame:
         """actions: integer tensor [n] in 0..3 (UP, DOWN, LEFT, RIGHT).
         Returns (boards, reward, done) -- the same tensors every call (updated in place), as
         the reference returns the same list object every call."""
-        a = as_actions(actions, self.device)
-        if a.numel() != self.n:
-            raise ValueError("expected %d actions, got %d" % (self.n, a.numel()))
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.r48_step(
-                self.boards.data_ptr(), a.data_ptr(), self.boards.data_ptr(), self.reward.data_ptr(),
-                self.done.data_ptr(), self.n, self.seed, self.board_base, self.steps,
-                self.reward_mode, self.status.data_ptr(), _stream(self.device)))
+        # fast path: a uint8 tensor already on this device goes straight to the C call (the
+        # Python side of a call is ~5 us; the kernel for 2^20 boards is ~11 us)
+        if not (torch.is_tensor(actions) and actions.dtype == torch.uint8 and actions.device == self.device
+                and actions.is_contiguous()):
+            actions = as_actions(actions, self.device)
+        if actions.numel() != self.n:
+            raise ValueError("expected %d actions, got %d" % (self.n, actions.numel()))
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.step(actions)
+        p = self._ptrs
+        rc = self._lib.r48_step(p[0], actions.data_ptr(), p[0], p[1], p[2], self.n, self.seed, self.board_base,
+                                self.steps, self.reward_mode, p[3], torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _native.check(rc)
         self.steps += 1
         return self.boards, self.reward, self.done
 
