@@ -464,3 +464,34 @@ def test_empty_and_tiny_batches(r48, orc):
         res = r48.random_rollouts(n, seed=2, board_base=3)
         fb, ln = orc.rollout(n, 2, 3)
         assert (to_u64(res.final_boards) == fb).all() and (res.lengths.cpu().numpy().view(np.uint32) == ln).all()
+
+
+def test_env_step_in_a_cuda_graph(r48, orc):
+    """env_step keeps its counters on the device, so a captured graph replayed k times is k real
+    steps (what INTEGRATION.md recommends for launch-bound policy loops)."""
+    n, k = 2049, 40
+    env = r48.BatchedGame(n, seed=SEED, board_base=11)
+    a = np.random.default_rng(12).integers(0, 4, n).astype(np.uint8)
+    d_a = dev(a)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        env.env_step(d_a)                                   # one real step (also allocates the env tensors)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):                               # capture runs nothing
+        env.env_step(d_a)
+    for _ in range(k):
+        g.replay()
+    torch.cuda.synchronize()
+    boards = orc.reset_batch(n, SEED, 11)
+    steps = np.zeros(n, np.uint32)
+    eps = np.zeros(n, np.uint32)
+    for _ in range(k + 1):
+        boards, steps, eps, o_r, o_d, _ = orc.env_step_batch(boards, a, steps, eps, SEED, 11, n)
+    assert (to_u64(env.boards) == boards).all()
+    assert (env.env_steps.cpu().numpy().view(np.uint32) == steps).all()
+    assert (env.env_episodes.cpu().numpy().view(np.uint32) == eps).all()
+    assert (env.done.cpu().numpy() == o_d).all()
+    assert (env.obs.cpu().numpy() == orc.decode_batch(boards, "float32")).all()
