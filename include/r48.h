@@ -18,8 +18,19 @@
  *     (a cudaStream_t passed as void*; NULL = legacy default stream).  No implicit sync.
  *   - Return value: 0 on success, a negative R48_ERR_* otherwise; nothing throws across
  *     the boundary.  r48_last_error() gives a thread-local message for the last failure.
- *   - Random draws come from Philox4x32-10 keyed by (seed, global board id, tick); the
- *     global id of element i of a batch is board_base + i.  See DESIGN.md "draw spec".
+ *   - Random draws come from Philox4x32-7 keyed by (seed, global board id, tick >> 2), one
+ *     32-bit word per tick; the global id of element i of a batch is board_base + i.  A spawn
+ *     counts the blanks in the order of the move's axis (row-major after LEFT/RIGHT,
+ *     column-major after UP/DOWN).  See DESIGN.md "draw spec".
+ *   - Domain edge: merging two 32768 tiles would give 65536, which has no nibble; the merge
+ *     SATURATES (the result is one 32768 tile, the other disappears, the board counts as
+ *     changed).  Transitions are bit-exact with the reference for every board that does not
+ *     merge two 32768 tiles.
+ *   - Threads: the device entry points keep no per-call state and may be called from any number
+ *     of host threads (each on its own stream).  The *_host entry points share one scratch
+ *     arena, two streams and two events per device and take a per-device mutex for the whole
+ *     call: concurrent calls on one device are safe and run one after another, calls on
+ *     different devices run concurrently.  r48_last_error() is thread-local.
  *   - reward_mode 0 = reference (reward is always 0, GameClient.py:138);
  *     reward_mode 1 = merge_sum (sum of the tiles created by merges; extension).
  */
@@ -32,7 +43,7 @@
 extern "C" {
 #endif
 
-#define R48_VERSION 100
+#define R48_VERSION 200
 
 #define R48_OK             0
 #define R48_ERR_NULL      -1   /* required pointer is NULL */
@@ -61,6 +72,9 @@ extern "C" {
 #define R48_ROLLOUT_WORKSPACE_BYTES 256
 
 int r48_version(void);
+/* "R48_BUILD_ID=<16 hex digits>": a hash of the sources this binary was compiled from (the
+ * Python loader refuses a library built from other sources). */
+const char *r48_build_id(void);
 const char *r48_last_error(void);
 
 /* Build the per-device row tables (idempotent; other calls do it lazily). */
@@ -83,7 +97,8 @@ int r48_step(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *
 
 /* The same with the spawn draws supplied by the caller (parity mode): spawn_k[i] is what
  * random.randint(0, n_blank-1) returned (GameClient.py:121), spawn_exp[i] is 1 for a 2,
- * 2 for a 4 (GameClient.py:125).  Both are ignored where the move changes nothing. */
+ * 2 for a 4 (GameClient.py:125).  Both are ignored where the move changes nothing; a spawn_k
+ * that is not below the number of blanks places nothing. */
 int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *spawn_k,
                       const uint8_t *spawn_exp, uint64_t *out, int32_t *reward, uint8_t *done,
                       int64_t n, int reward_mode, int32_t *status, void *stream);
@@ -103,13 +118,24 @@ int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint3
                  int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
                  int reward_mode, int auto_reset, int32_t *status, void *stream);
 
+/* r48_env_step that also appends every env's transition (board before the step, action, reward,
+ * board after the step -- the finished board, not the auto-reset one -- and done) to a
+ * transition ring (see r48_ring below; n <= 2^30).  ring == NULL: plain r48_env_step. */
+struct r48_ring;
+int r48_env_step_ring(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
+                      int32_t *reward, uint8_t *done, float *obs, int obs_mode,
+                      uint64_t *final_boards, int64_t n, uint64_t seed, uint64_t board_base,
+                      uint64_t id_stride, int reward_mode, int auto_reset, int32_t *status,
+                      const struct r48_ring *ring, void *stream);
+
 /* Game.random_fill_grid alone (GameClient.py:102-127) with injected draws: put exponent
- * spawn_exp[i] into the spawn_k[i]-th blank (row-major) of boards[i]; k >= n_blank leaves
- * the board as it is (a full board is returned unchanged, GameClient.py:117-118). */
+ * spawn_exp[i] into the spawn_k[i]-th blank (row-major) of boards[i]; any k >= n_blank (up to
+ * 255) leaves the board as it is (a full board is returned unchanged, GameClient.py:117-118). */
 int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,
                        int64_t n, void *stream);
 
-/* The same with the draws made on the GPU from the Philox words of (seed, board, tick). */
+/* The same with the draws made on the GPU from the Philox word of (seed, board, tick); there is
+ * no move here, so the blanks are counted row-major. */
 int r48_spawn(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, uint32_t tick,
               void *stream);
 
@@ -162,6 +188,10 @@ int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int 
 int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int64_t n,
                       uint64_t *stats, void *stream);
 
+/* The packed per-episode record described at r48_rollout_host_ex, on the device. */
+int r48_episode_records(const uint64_t *final_boards, const uint32_t *lengths, uint32_t *records,
+                        int64_t n, void *stream);
+
 /* np.sum(state_matrix) (main.py:48) and the largest tile's exponent, per board. */
 int r48_scores(const uint64_t *boards, uint32_t *score, uint8_t *max_exp, int64_t n,
                void *stream);
@@ -174,6 +204,53 @@ int r48_decode_i32(const uint64_t *boards, int32_t *out, int64_t n, void *stream
 int r48_encode_i32(const int32_t *values, uint64_t *boards, int64_t n, int32_t *status,
                    void *stream);
 
+/* ---- transition ring: Replay (algorithm/ddpg/replay.py:8-47) for batches, on the device ----
+ * Five caller-owned device arrays of `capacity` slots plus a two-word device cursor
+ * (cursor[0] = transitions appended since the last clear, cursor[1] = scratch, both zero
+ * initially).  The struct itself lives in HOST memory.  The cursor lives on the device so that
+ * appends and samples need no host synchronisation and can be captured in CUDA graphs. */
+typedef struct r48_ring {
+    uint64_t *state;        /* board before the step            (ddpg.py:31 `state`)      */
+    uint8_t  *action;
+    int32_t  *reward;
+    uint64_t *next_state;   /* board after the step, a distinct value (ddpg.py:29-31 stores
+                               the SAME list object twice; that aliasing is not reproduced) */
+    uint8_t  *done;
+    uint64_t *cursor;       /* [2] */
+    uint64_t  capacity;     /* Replay.max_size (replay.py:11) */
+} r48_ring;
+
+/* Replay.clear (replay.py:45-47). */
+int r48_ring_clear(const r48_ring *ring, void *stream);
+
+/* Replay.store (replay.py:18-21) for n transitions.  drop_when_full != 0 is the reference's
+ * rule (a full buffer ignores new transitions: the first capacity - size of the batch are kept);
+ * drop_when_full == 0 overwrites the oldest slot, transition i going to slot
+ * (cursor + i) % capacity.  reward / done may be NULL (stored as 0). */
+int r48_ring_append(const r48_ring *ring, const uint64_t *state, const uint8_t *action,
+                    const int32_t *reward, const uint64_t *next_state, const uint8_t *done,
+                    int64_t n, int drop_when_full, void *stream);
+
+/* Replay.sample (replay.py:23-27, random.sample of :33) without its clear(): gathers `batch`
+ * transitions from the size = min(cursor, capacity) valid slots.
+ *   with_replacement == 0: distinct slots (element i is slot perm(i) of a keyed permutation of
+ *     [0, size)); elements i >= size are skipped and get out_index -1 (the reference returns
+ *     the whole list when asked for more than it holds);
+ *   with_replacement != 0: independent uniform slots.
+ * Draws are keyed by (seed, draw, element): the same arguments give the same sample.
+ * out_index (optional) receives the slot numbers; obs_state / obs_next_state (optional) receive
+ * the float32 [batch][4][4] readouts (tile values, or exponents when obs_mode = 1). */
+int r48_ring_sample(const r48_ring *ring, int64_t batch, uint64_t seed, uint64_t draw,
+                    int with_replacement, int64_t *out_index, uint64_t *out_state,
+                    uint8_t *out_action, int32_t *out_reward, uint64_t *out_next_state,
+                    uint8_t *out_done, float *obs_state, float *obs_next_state, int obs_mode,
+                    void *stream);
+
+/* Measurement aid (bench.py): moves the single-step kernel's 22 bytes per board (reads boards +
+ * actions, writes boards + reward + done) and computes nothing. */
+int r48_debug_copy22(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
+                     uint8_t *done, int64_t n, void *stream);
+
 /* ---- host-buffer entry points (what a CPU-side caller of the reference would bind) ----
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous); the
  * library stages through a per-device scratch arena it owns, runs the kernels on its own
@@ -185,6 +262,16 @@ int r48_afterstates_host(const uint64_t *in, uint64_t *out, int32_t *reward, uin
                          uint8_t *done, int64_t n, int reward_mode, int device);
 int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
                      uint32_t *lengths, uint64_t *stats, int device);
+/* r48_rollout_host with the policy and the per-episode outputs selectable: any of final_boards
+ * (8 B), lengths (4 B) and records (4 B) may be NULL and is then not computed / copied.
+ * records[i] packs what main.py:48 prints per game and the episode length into one word:
+ *     bits 31..13  score / 2   (score = np.sum(state_matrix); always even, at most 2^19: exact)
+ *     bits 12..0   min(length, 8191) */
+#define R48_RECORD_SCORE(r)  (((uint32_t)(r) >> 13) << 1)
+#define R48_RECORD_LENGTH(r) ((uint32_t)(r) & 8191u)
+int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int policy,
+                        uint64_t *final_boards, uint32_t *lengths, uint32_t *records,
+                        uint64_t *stats, int device);
 /* Release the scratch arena and tables of every device. */
 int r48_shutdown(void);
 

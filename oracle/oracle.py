@@ -57,11 +57,21 @@ def lib():
     L.orc_move.restype = C.c_uint64
     L.orc_game_over.argtypes = [C.c_uint64]
     L.orc_game_over.restype = C.c_int
-    L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
-    L.orc_philox4x32_10.restype = None
-    L.orc_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32,
-                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
-    L.orc_draw.restype = None
+    L.orc_random_fill_grid_colmajor.argtypes = [i64p, C.c_int, C.c_int64]
+    L.orc_random_fill_grid_colmajor.restype = C.c_int
+    L.orc_philox4x32.argtypes = [u32p, u32p, C.c_int, u32p]
+    L.orc_philox4x32.restype = None
+    L.orc_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+    L.orc_draw.restype = C.c_uint32
+    L.orc_spawn.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    L.orc_spawn.restype = C.c_uint64
+    L.orc_episode_records.argtypes = [u64p, u32p, C.c_int64, u32p]
+    L.orc_episode_records.restype = None
+    L.orc_ring_append.argtypes = [u64p, u8p, i32p, u64p, u8p, u64p, C.c_uint64, u64p, u8p, C.c_void_p, u64p,
+                                  C.c_void_p, C.c_int64, C.c_int]
+    L.orc_ring_append.restype = None
+    L.orc_ring_sample_indices.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, i64p]
+    L.orc_ring_sample_indices.restype = None
     L.orc_reset.argtypes = [C.c_uint64, C.c_uint64]
     L.orc_reset.restype = C.c_uint64
     L.orc_reset_batch.argtypes = [u64p, C.c_int64, C.c_uint64, C.c_uint64]
@@ -163,16 +173,34 @@ def game_over(board):
     return bool(lib().orc_game_over(int(board)))
 
 
-def philox(ctr, key):
+def random_fill_grid_colmajor(matrix, k, value):
+    m = _flat(matrix).copy()
+    n = lib().orc_random_fill_grid_colmajor(m, int(k), int(value))
+    if n < 0:
+        raise ValueError("k out of range")
+    return m.reshape(4, 4), n
+
+
+DRAW_ROUNDS = 7
+SPAWN4_THRESHOLD = 0x1999999A
+VALUE_HASH = 0x9E3779B1
+
+
+def philox(ctr, key, rounds=DRAW_ROUNDS):
     out = np.zeros(4, np.uint32)
-    lib().orc_philox4x32_10(np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), out)
+    lib().orc_philox4x32(np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), int(rounds), out)
     return out
 
 
 def draw(seed, board_id, tick):
-    a, v = C.c_uint32(0), C.c_uint32(0)
-    lib().orc_draw(int(seed), int(board_id), int(tick), C.byref(a), C.byref(v))
-    return int(a.value), int(v.value)
+    """The tick's Philox word: action = a >> 30, cell from a << 2, value from a * VALUE_HASH."""
+    return int(lib().orc_draw(int(seed), int(board_id), int(tick)))
+
+
+def spawn_batch(boards, seed, board_base, tick):
+    L = lib()
+    return np.array([L.orc_spawn(int(b), int(seed), int(board_base) + i, int(tick))
+                     for i, b in enumerate(boards)], np.uint64)
 
 
 # ---------------------------------------------------------------- batch forms
@@ -303,3 +331,44 @@ def scores(final_boards):
 def max_exps(final_boards):
     L = lib()
     return np.array([L.orc_max_exp(int(b)) for b in final_boards], np.uint8)
+
+
+def episode_records(final_boards, lengths):
+    fb = np.ascontiguousarray(final_boards, np.uint64)
+    ln = np.ascontiguousarray(lengths, np.uint32)
+    out = np.zeros(fb.size, np.uint32)
+    lib().orc_episode_records(fb, ln, fb.size, out)
+    return out
+
+
+# ---------------------------------------------------------------- transition ring (Replay)
+
+class Ring:
+    """CPU restatement of the device transition ring (algorithm/ddpg/replay.py:8-47)."""
+
+    def __init__(self, capacity):
+        self.capacity = int(capacity)
+        self.state = np.zeros(capacity, np.uint64)
+        self.action = np.zeros(capacity, np.uint8)
+        self.reward = np.zeros(capacity, np.int32)
+        self.next_state = np.zeros(capacity, np.uint64)
+        self.done = np.zeros(capacity, np.uint8)
+        self.cursor = np.zeros(1, np.uint64)
+
+    def append(self, state, action, reward, next_state, done, drop_when_full=False):
+        state = np.ascontiguousarray(state, np.uint64)
+        reward = np.ascontiguousarray(reward, np.int32)
+        done = np.ascontiguousarray(done, np.uint8)
+        lib().orc_ring_append(self.state, self.action, self.reward, self.next_state, self.done, self.cursor,
+                              self.capacity, state, np.ascontiguousarray(action, np.uint8),
+                              reward.ctypes.data, np.ascontiguousarray(next_state, np.uint64),
+                              done.ctypes.data, state.size, int(bool(drop_when_full)))
+
+    def size(self):
+        return int(min(int(self.cursor[0]), self.capacity))
+
+    def sample_indices(self, batch, seed, draw_id, with_replacement=False):
+        out = np.zeros(batch, np.int64)
+        lib().orc_ring_sample_indices(int(self.cursor[0]), self.capacity, batch, int(seed), int(draw_id),
+                                      int(bool(with_replacement)), out)
+        return out

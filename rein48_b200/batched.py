@@ -28,8 +28,20 @@ def _require_cuda(device):
     return device
 
 
+def from_any(x):
+    """A torch tensor for `x` WITHOUT copying when x is a tensor, an object that speaks DLPack
+    (`__dlpack__`: cupy / jax / numba arrays, other frameworks' tensors) or a DLPack capsule
+    (torch.utils.dlpack.to_dlpack); anything else is returned as it came."""
+    if torch.is_tensor(x):
+        return x
+    if hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule":
+        return torch.utils.dlpack.from_dlpack(x)
+    return x
+
+
 def as_actions(actions, device):
     """Any integer tensor/sequence -> uint8 device tensor (values are checked on the GPU)."""
+    actions = from_any(actions)
     if not torch.is_tensor(actions):
         actions = torch.as_tensor(actions)
     if actions.dtype != torch.uint8:
@@ -44,6 +56,14 @@ class BatchedGame:
 
     seed / board_base key the Philox stream: board i of this batch is global board
     board_base + i, so shards of one logical batch on different GPUs draw disjoint streams.
+    id_stride = the size of the WHOLE logical batch (all shards): env_step() gives episode e of
+    env i the id board_base + i + e * id_stride, so it must be the same on every shard and at
+    least the world batch, or shards replay each other's streams one episode apart.  It
+    defaults to n for an unsharded batch (board_base == 0).
+
+    Every reset() after the first starts a new EPOCH: the Philox key becomes
+    seed + epoch * 0x9E3779B97F4A7C15 (mod 2^64), so a loop that calls reset() per episode (the
+    a3c / ddpg workers do) sees fresh games each time, reproducibly from (seed, epoch).
     """
 
     state_space_size = 4          # GameClient.py:21-27
@@ -54,11 +74,18 @@ class BatchedGame:
     action_size = 4
     reward_size = 1
 
-    def __init__(self, n, seed=0, device="cuda", board_base=0, reward_mode="reference"):
+    EPOCH_KEY_STEP = 0x9E3779B97F4A7C15
+
+    def __init__(self, n, seed=0, device="cuda", board_base=0, reward_mode="reference", id_stride=None):
         self.device = _require_cuda(device)
         self.n = int(n)
-        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.seed0 = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.seed = self.seed0
+        self.epoch = -1
         self.board_base = int(board_base)
+        if id_stride is not None and int(id_stride) < self.n:
+            raise ValueError("id_stride must be at least the batch size")
+        self.id_stride = int(id_stride) if id_stride is not None else (self.n if self.board_base == 0 else None)
         self.reward_mode = REWARD_MODES[reward_mode]
         self._lib = _native.lib()
         with torch.cuda.device(self.device):
@@ -72,11 +99,17 @@ class BatchedGame:
         self.reset()
 
     # -- Game.reset (GameClient.py:33-38): one tile per board
-    def reset(self):
+    def reset(self, epoch=None):
+        """New games on every board.  `epoch` (default: the next one) selects the draw stream."""
+        self.epoch = self.epoch + 1 if epoch is None else int(epoch)
+        self.seed = (self.seed0 + self.epoch * self.EPOCH_KEY_STEP) & 0xFFFFFFFFFFFFFFFF
         with torch.cuda.device(self.device):
             _native.check(self._lib.r48_reset(self.boards.data_ptr(), self.n, self.seed,
                                               self.board_base, _stream(self.device)))
-        self.done.zero_()
+            self.done.zero_()
+            if hasattr(self, "env_steps"):            # the per-env counters of env_step() restart too
+                self.env_steps.zero_()
+                self.env_episodes.zero_()
         self.steps = 0
         return self.boards
 
@@ -89,7 +122,7 @@ class BatchedGame:
         # Python side of a call is ~5 us; the kernel for 2^20 boards is ~11 us)
         if not (torch.is_tensor(actions) and actions.dtype == torch.uint8 and actions.device == self.device
                 and actions.is_contiguous()):
-            actions = as_actions(actions, self.device)
+            actions = as_actions(actions, self.device)      # DLPack producers come in here, zero-copy
         if actions.numel() != self.n:
             raise ValueError("expected %d actions, got %d" % (self.n, actions.numel()))
         if torch.cuda.current_device() != self.device.index:
@@ -117,27 +150,40 @@ class BatchedGame:
         return self.boards, self.reward, self.done
 
     # -- vectorised-env form: per-env counters, auto-reset, fused observation
-    def env_step(self, actions, auto_reset=True, obs=True, log2=False, id_stride=None):
+    def env_step(self, actions, auto_reset=True, obs=True, log2=False, id_stride=None, ring=None):
         """Game.step for every env with its OWN tick/episode counters; finished games are reset
         in place when auto_reset (done[i] = 1 then comes with the new episode's first board,
         the finished board is kept in `self.final_boards`).  Returns (obs or boards, reward,
-        done).  Do not mix with step() on the same object: that one keys all boards by one
-        shared step counter."""
+        done).  `ring` (a ReplayRing) receives every env's transition in the same kernel.
+        Do not mix with step() on the same object: that one keys all boards by one shared step
+        counter."""
         a = as_actions(actions, self.device)
         if a.numel() != self.n:
             raise ValueError("expected %d actions, got %d" % (self.n, a.numel()))
+        stride = id_stride if id_stride is not None else self.id_stride
+        if stride is None:
+            raise ValueError("this batch is a shard (board_base != 0): pass id_stride = the size of the whole "
+                             "logical batch to the constructor, so that shards do not reuse each other's ids")
+        if ring is not None:
+            if ring.device != self.device:
+                raise ValueError("the ring lives on %s, the environments on %s" % (ring.device, self.device))
+            if ring.mode != "ring":
+                raise ValueError("the fused append overwrites the oldest slot; a mode='reference' ring takes "
+                                 "transitions through ReplayRing.store")
         with torch.cuda.device(self.device):
             if not hasattr(self, "env_steps"):
                 self.env_steps = torch.zeros(self.n, dtype=torch.int32, device=self.device)
                 self.env_episodes = torch.zeros(self.n, dtype=torch.int32, device=self.device)
                 self.final_boards = torch.zeros(self.n, dtype=torch.int64, device=self.device)
                 self.obs = torch.empty((self.n, 4, 4), dtype=torch.float32, device=self.device)
-            _native.check(self._lib.r48_env_step(
+            _native.check(self._lib.r48_env_step_ring(
                 self.boards.data_ptr(), a.data_ptr(), self.env_steps.data_ptr(), self.env_episodes.data_ptr(),
                 self.reward.data_ptr(), self.done.data_ptr(), self.obs.data_ptr() if obs else None,
                 int(bool(log2)), self.final_boards.data_ptr(), self.n, self.seed, self.board_base,
-                int(id_stride if id_stride is not None else self.n), self.reward_mode, int(bool(auto_reset)),
-                self.status.data_ptr(), _stream(self.device)))
+                int(stride), self.reward_mode, int(bool(auto_reset)),
+                self.status.data_ptr(), ring._ref() if ring is not None else None, _stream(self.device)))
+            if ring is not None:
+                ring._appended(self.n)
         return (self.obs if obs else self.boards), self.reward, self.done
 
     def check_actions(self):
@@ -163,6 +209,9 @@ class BatchedGame:
 # ---------------------------------------------------------------------- functional forms
 
 def _i64(boards):
+    boards = from_any(boards)
+    if not torch.is_tensor(boards):
+        raise TypeError("boards must be a CUDA tensor (or a DLPack producer) of int64/uint64 bit patterns")
     if boards.dtype not in (torch.int64, torch.uint64):
         raise TypeError("boards must be int64/uint64 bit patterns")
     if not boards.is_cuda:
@@ -208,6 +257,7 @@ def decode(boards, dtype=torch.float32, log2=False):
 
 def encode(values):
     """[n,4,4] int32 tile values on the GPU -> packed boards; ValueError on illegal tiles."""
+    values = from_any(values)
     if not values.is_cuda:
         raise RuntimeError("values must live on a CUDA device; there is no CPU path")
     values = values.to(torch.int32).contiguous()

@@ -12,6 +12,16 @@
 #pragma once
 #include <stdint.h>
 
+// Build-time switches (A/B-timed on a B200, see DESIGN.md "measured and rejected"):
+//   R48_FMA_INDEX  table addresses by IMAD.WIDE / IMAD.HI (FMA pipe) instead of SHF + LOP3 (ALU pipe)
+//   R48_SWIZZLE    XOR bits 7..11 of the row into the bank bits of its table slot
+#ifndef R48_FMA_INDEX
+#define R48_FMA_INDEX 0
+#endif
+#ifndef R48_SWIZZLE
+#define R48_SWIZZLE 0
+#endif
+
 namespace r48 {
 
 // ------------------------------------------------------------------ small helpers
@@ -54,12 +64,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     return v;
 }
 
-// ------------------------------------------------------------------ Philox4x32-10
-// Salmon et al., SC'11.  The ten round keys depend only on the seed, so the host
-// precomputes them and they arrive as kernel parameters (constant bank operands).
+// ------------------------------------------------------------------ Philox4x32-7
+// Salmon et al., SC'11 (Random123 philox4x32, 7 rounds: the smallest round count the paper reports
+// as passing BigCrush; KATs in tests/test_oracle_golden.py).  The round keys depend only on the
+// seed, so the host precomputes them and they arrive as kernel parameters (constant bank operands).
+constexpr int kPhiloxRounds = 7;
+
 struct PhiloxKeys {
-    uint32_t k0[10];
-    uint32_t k1[10];
+    uint32_t k0[kPhiloxRounds];
+    uint32_t k1[kPhiloxRounds];
 };
 
 #define R48_PHILOX_M0 0xD2511F53u
@@ -67,12 +80,13 @@ struct PhiloxKeys {
 #define R48_PHILOX_W0 0x9E3779B9u
 #define R48_PHILOX_W1 0xBB67AE85u
 #define R48_SPAWN4_THRESHOLD 0x1999999Au      // ceil(0.1 * 2^32): P(tile 4) = 0.1
+#define R48_VALUE_HASH 0x9E3779B1u            // odd: a -> a * HASH mod 2^32 is a bijection
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              const PhiloxKeys &K, uint32_t (&w)[4])
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           const PhiloxKeys &K, uint32_t (&w)[4])
 {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < kPhiloxRounds; r++) {
         uint64_t p0 = (uint64_t)R48_PHILOX_M0 * c0;
         uint64_t p1 = (uint64_t)R48_PHILOX_M1 * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
@@ -85,9 +99,36 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
 
-// The same function split for a caller that makes many calls with the same (c0, c1, c3 = 0) and a
-// varying c2 -- the rollout kernel: (id.lo, id.hi, tick >> 1, 0).  Round 0's M0*c0 product and
-// round 1's M1*c2 product then depend only on the episode, so they are computed once per episode.
+// Draw spec: tick t of board `id` uses call (id.lo, id.hi, t >> 2, 0) and
+// its word a = w[t & 3]:
+//   action = a >> 30
+//   cell   = the k-th blank, k = mulhi(a << 2, n_blank), counted in the order of the tick's move
+//            axis (row-major for LEFT/RIGHT, column-major for UP/DOWN)
+//   value  = 4 if a * R48_VALUE_HASH (mod 2^32) < THRESHOLD else 2
+__device__ __forceinline__ uint32_t draw_word(uint64_t id, uint32_t tick, const PhiloxKeys &K)
+{
+    uint32_t w[4];
+    philox4x32((uint32_t)id, (uint32_t)(id >> 32), tick >> 2, 0u, K, w);
+    const uint32_t j = tick & 3u;
+    return j == 0u ? w[0] : j == 1u ? w[1] : j == 2u ? w[2] : w[3];
+}
+
+// exponent of the spawned tile (2 for a "4", 1 for a "2") as v29 = exponent << 29 (see
+// place_tile_v29); 0 when nothing is spawned
+__device__ __forceinline__ uint32_t spawn_v29(uint32_t a, bool changed)
+{
+    const uint32_t v = (a * R48_VALUE_HASH < R48_SPAWN4_THRESHOLD) ? (2u << 29) : (1u << 29);
+    return changed ? v : 0u;
+}
+
+__device__ __forceinline__ uint32_t spawn_exp(uint32_t a)
+{
+    return (a * R48_VALUE_HASH < R48_SPAWN4_THRESHOLD) ? 2u : 1u;
+}
+
+// --- the call split for the rollout kernel: (c0, c1, c3 = 0) are fixed for an episode and only
+// c2 = tick >> 2 varies, so round 0's M0*c0 product and round 1's M1*c2 product are computed once
+// per episode.
 struct PhiloxEpisode {
     uint32_t p0lo;      // lo(M0 * c0)                      -> c3 entering round 1
     uint32_t q1lo;      // lo(M1 * (hi(M0*c0) ^ k1[0]))     -> c1 entering round 2
@@ -102,9 +143,8 @@ __device__ __forceinline__ PhiloxEpisode philox_episode(uint32_t c0, const Philo
     return PhiloxEpisode{(uint32_t)p0, (uint32_t)q1, (uint32_t)(q1 >> 32)};
 }
 
-__device__ __forceinline__ void philox4x32_10_episode(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                       const PhiloxEpisode &E, const PhiloxKeys &K,
-                                                       uint32_t (&w)[4])
+__device__ __forceinline__ void philox4x32_episode(uint32_t c1, uint32_t c2, const PhiloxEpisode &E,
+                                                   const PhiloxKeys &K, uint32_t (&w)[4])
 {
     // round 0 (M0*c0 and n2 come from E)
     const uint64_t a1 = (uint64_t)R48_PHILOX_M1 * c2;
@@ -115,9 +155,8 @@ __device__ __forceinline__ void philox4x32_10_episode(uint32_t c0, uint32_t c1, 
     uint32_t y0 = E.q1hi ^ x1 ^ K.k0[1];
     uint32_t y2 = (uint32_t)(b0 >> 32) ^ E.p0lo ^ K.k1[1];
     uint32_t y1 = E.q1lo, y3 = (uint32_t)b0;
-    (void)c0;
 #pragma unroll
-    for (int r = 2; r < 10; r++) {
+    for (int r = 2; r < kPhiloxRounds; r++) {
         const uint64_t p0 = (uint64_t)R48_PHILOX_M0 * y0;
         const uint64_t p1 = (uint64_t)R48_PHILOX_M1 * y2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ y1 ^ K.k0[r];
@@ -130,16 +169,57 @@ __device__ __forceinline__ void philox4x32_10_episode(uint32_t c0, uint32_t c1, 
     w[0] = y0; w[1] = y1; w[2] = y2; w[3] = y3;
 }
 
-// Draw spec: tick t of board `id` uses call (id.lo, id.hi, t >> 1, 0) and the
-// word pair (2*(t&1), 2*(t&1)+1) = (a, v): action = a >> 30, cell = mulhi(a << 2, n_blank),
-// value = v < THRESHOLD ? 4 : 2.
-__device__ __forceinline__ void draw_words(uint64_t id, uint32_t tick, const PhiloxKeys &K,
-                                           uint32_t &a, uint32_t &v)
+// --- the call split for the single-step kernels: every board of a launch is at the same tick and
+// (the host splits launches at multiples of 2^32 ids) has the same id.hi, so c1, c2, c3 are
+// launch constants.  The host folds them through rounds 0 and 1 (make_philox_launch) and the
+// device computes only the id.lo-dependent half of those rounds and, in the last round, only
+// the word the tick uses: 23 instructions per board instead of 29.
+struct PhiloxLaunch {
+    uint32_t r0_n0;     // c0 entering round 1: hi(M1*c2) ^ c1 ^ k0[0]
+    uint32_t r1_c1k;    // lo(M1*c2) ^ k0[1]            (c1 entering round 1, key folded in)
+    uint32_t r1_h0k;    // hi(M0*r0_n0) ^ k1[1]
+    uint32_t r2_c3k;    // lo(M0*r0_n0) ^ k1[2]         (c3 entering round 2, key folded in)
+    uint32_t word;      // tick & 3
+};
+
+__device__ __forceinline__ uint32_t philox_launch_word(uint32_t id_lo, const PhiloxLaunch &P,
+                                                       const PhiloxKeys &K)
 {
-    uint32_t w[4];
-    philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), tick >> 1, 0u, K, w);
-    a = (tick & 1u) ? w[2] : w[0];
-    v = (tick & 1u) ? w[3] : w[1];
+    // round 0: only M0*c0 varies
+    const uint64_t p0 = (uint64_t)R48_PHILOX_M0 * id_lo;
+    const uint32_t a2 = (uint32_t)(p0 >> 32) ^ K.k1[0];           // c2 entering round 1 (c3 = 0)
+    const uint32_t a3 = (uint32_t)p0;                             // c3 entering round 1
+    // round 1: c0 = r0_n0 is a launch constant
+    const uint64_t q1 = (uint64_t)R48_PHILOX_M1 * a2;
+    uint32_t y0 = (uint32_t)(q1 >> 32) ^ P.r1_c1k;
+    uint32_t y1 = (uint32_t)q1;
+    uint32_t y2 = a3 ^ P.r1_h0k;
+    // round 2: c3 is a launch constant
+    {
+        const uint64_t p0b = (uint64_t)R48_PHILOX_M0 * y0;
+        const uint64_t p1b = (uint64_t)R48_PHILOX_M1 * y2;
+        const uint32_t n0 = (uint32_t)(p1b >> 32) ^ y1 ^ K.k0[2];
+        const uint32_t n2 = (uint32_t)(p0b >> 32) ^ P.r2_c3k;
+        y1 = (uint32_t)p1b;
+        y0 = n0; y2 = n2;
+        uint32_t y3 = (uint32_t)p0b;
+#pragma unroll
+        for (int r = 3; r < kPhiloxRounds - 1; r++) {
+            const uint64_t p0c = (uint64_t)R48_PHILOX_M0 * y0;
+            const uint64_t p1c = (uint64_t)R48_PHILOX_M1 * y2;
+            const uint32_t m0 = (uint32_t)(p1c >> 32) ^ y1 ^ K.k0[r];
+            const uint32_t m2 = (uint32_t)(p0c >> 32) ^ y3 ^ K.k1[r];
+            y1 = (uint32_t)p1c;
+            y3 = (uint32_t)p0c;
+            y0 = m0; y2 = m2;
+        }
+        // last round: one word (P.word is launch-uniform, so this is a uniform branch)
+        constexpr int L = kPhiloxRounds - 1;
+        if (P.word == 0u) return __umulhi(R48_PHILOX_M1, y2) ^ y1 ^ K.k0[L];
+        if (P.word == 1u) return R48_PHILOX_M1 * y2;
+        if (P.word == 2u) return __umulhi(R48_PHILOX_M0, y0) ^ y3 ^ K.k1[L];
+        return R48_PHILOX_M0 * y0;
+    }
 }
 
 // ------------------------------------------------------------------ board symmetries
@@ -161,19 +241,23 @@ __device__ __forceinline__ uint32_t nibswap(uint32_t w)
     return bsel(0xF0F0F0F0u, w << 4, w >> 4);
 }
 
-// ------------------------------------------------------------------ the move, 16-bit tables
-// (reward_mode 1 kernels).  One lookup per row: left[r] = row r after a LEFT move (toward
-// nibble 0).  RIGHT = reverse rows, LEFT, reverse; UP/DOWN = transpose, LEFT/RIGHT,
-// transpose.  `merges`: two 4-bit exponents of the merged pairs of the row.
+// ------------------------------------------------------------------ the move
+// A move is "slide the ROWS of the stored board toward nibble 0 (LEFT) or nibble 3 (RIGHT)".
+// UP/DOWN are the same thing on the transposed board: `orient` transposes for a vertical action,
+// and the callers decide when to transpose back (the single-step kernels right after the spawn,
+// the fused rollout only when the next move's axis differs).
 
+__device__ __forceinline__ bool is_vertical(uint32_t action) { return action < 2u; }      // UP, DOWN
+__device__ __forceinline__ bool is_toward_high(uint32_t action) { return (action & 1u) != 0u; }  // DOWN, RIGHT
+
+// --- 16-bit tables (reward_mode 1 kernels).  One lookup per row: left[r] = row r after a LEFT
+// move; RIGHT = reverse the row, LEFT, reverse.  `merges`: two 4-bit exponents of the merged
+// pairs of the row.
 template <bool WITH_REWARD>
-__device__ __forceinline__ void move_l16(uint32_t &lo, uint32_t &hi, uint32_t action,
-                                     const uint16_t *__restrict__ left,
-                                     const uint8_t *__restrict__ merges, uint32_t &reward)
+__device__ __forceinline__ void rows_l16(uint32_t &lo, uint32_t &hi, bool toward_high,
+                                         const uint16_t *__restrict__ left,
+                                         const uint8_t *__restrict__ merges, uint32_t &reward)
 {
-    const bool vertical = action < 2u;
-    const bool toward_high = (action & 1u) != 0u;      // DOWN or RIGHT
-    if (vertical) transpose(lo, hi);
     if (toward_high) { lo = nibswap(lo); hi = nibswap(hi); }
     // row -> table index; for reversed rows the PRMT also swaps the two bytes
     const uint32_t ex0 = toward_high ? 0x4401u : 0x4410u;
@@ -193,12 +277,10 @@ __device__ __forceinline__ void move_l16(uint32_t &lo, uint32_t &hi, uint32_t ac
     lo = prmt(o0, o1, pk);
     hi = prmt(o2, o3, pk);
     if (toward_high) { lo = nibswap(lo); hi = nibswap(hi); }
-    if (vertical) transpose(lo, hi);
 }
 
-// ------------------------------------------------------------------ the move, LR table
-// (reward_mode 0 kernels: step, afterstates, rollout).  lr[r] = LEFT result of row r in the
-// low half, RIGHT result in the high half, for r < kLrRows (rows whose last cell is below
+// --- LR table (reward_mode 0 kernels: step, afterstates, rollout).  lr[r] = LEFT result of row r
+// in the low half, RIGHT result in the high half, for r < kLrRows (rows whose last cell is below
 // 2^14 -- 224 KB, what fits beside nothing else in one SM's shared memory).  One lookup per
 // row serves both directions, so there is no row reversal; the PRMT that re-packs two rows
 // picks the half.  Rows outside the table (a 16384 or 32768 tile in the last cell) take a
@@ -206,28 +288,74 @@ __device__ __forceinline__ void move_l16(uint32_t &lo, uint32_t &hi, uint32_t ac
 
 constexpr uint32_t kLrRows = 0xE000u;               // 57344 entries x 4 B = 229376 B
 
+// slot of row r in the LR table.  With R48_SWIZZLE bits 7..11 of the row (cells 1..2) are folded
+// into the low five bits -- the shared-memory bank -- which otherwise come from cell 0 alone and
+// cluster on the few small exponents that dominate real boards.
+__host__ __device__ __forceinline__ uint32_t lr_slot(uint32_t r)
+{
+#if R48_SWIZZLE
+    return r ^ ((r >> 7) & 31u);
+#else
+    return r;
+#endif
+}
+
+// multipliers that turn shifts into FMA-pipe multiplies; they arrive as kernel parameters so that
+// ptxas cannot strength-reduce them back into shifts
+struct PipeConsts {
+    uint32_t m16, m18;          // 1 << 16, 1 << 18
+};
+
+// byte offsets (4 * slot) of the two rows of a word
+__device__ __forceinline__ void row_offsets(uint32_t w, const PipeConsts &pc, uint32_t &a0, uint32_t &a1)
+{
+#if R48_FMA_INDEX
+    uint32_t plo, phi;                                   // w * 2^16 = (w >> 16) : (w << 16)
+    asm("{\n.reg .u64 t;\nmul.wide.u32 t, %2, %3;\nmov.b64 {%0, %1}, t;\n}" : "=r"(plo), "=r"(phi) : "r"(w), "r"(pc.m16));
+    a0 = __umulhi(plo, pc.m18);                          // ((w << 16) * 2^18) >> 32 = (w & 0xFFFF) * 4
+    a1 = phi * 4u;
+#if R48_SWIZZLE
+    a0 ^= (plo >> 21) & 0x7Cu;                           // (row >> 7 & 31) << 2
+    a1 ^= (phi >> 5) & 0x7Cu;
+#endif
+#else
+    a0 = (w << 2) & 0x3FFFCu;
+    a1 = (w >> 14) & 0x3FFFCu;
+#if R48_SWIZZLE
+    a0 ^= (w >> 5) & 0x7Cu;
+    a1 ^= (w >> 21) & 0x7Cu;
+#endif
+#endif
+}
+
+// compress / merge-once / compress of one row, toward nibble 0 or toward nibble 3; all in
+// registers (no local array), out of line: it runs only for rows outside the table
 __device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
 {
-    // compress / merge-once / compress, toward nibble 0 or toward nibble 3
-    uint32_t c[4], n = 0, out = 0, o = 0;
+    if (toward_high) r = ((r & 0xFu) << 12) | ((r & 0xF0u) << 4) | ((r >> 4) & 0xF0u) | ((r >> 12) & 0xFu);
+    uint32_t packed = 0, n = 0;                     // non-empty cells, packed toward nibble 0
+#pragma unroll
     for (int t = 0; t < 4; t++) {
-        const uint32_t e = (r >> (4 * (toward_high ? 3 - t : t))) & 15u;
-        if (e) c[n++] = e;
+        const uint32_t e = (r >> (4 * t)) & 15u;
+        if (e) { packed |= e << (4 * n); n++; }
     }
-    for (uint32_t t = 0; t < n;) {
-        uint32_t e = c[t];
-        if (t + 1 < n && c[t] == c[t + 1]) { e = e + 1 > 15u ? 15u : e + 1; t += 2; }
-        else t += 1;
-        out |= e << (4 * (toward_high ? 3 - o : o));
+    uint32_t out = 0, o = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {                   // at most 4 output cells
+        const uint32_t e = packed & 15u, f = (packed >> 4) & 15u;
+        if (e == 0u) break;
+        if (e == f) { out |= (e + 1u > 15u ? 15u : e + 1u) << (4 * o); packed >>= 8; }
+        else { out |= e << (4 * o); packed >>= 4; }
         o++;
     }
+    if (toward_high) out = ((out & 0xFu) << 12) | ((out & 0xF0u) << 4) | ((out >> 4) & 0xF0u) | ((out >> 12) & 0xFu);
     return out;
 }
 
 // `lr` below is the shared-window byte address of the staged table (smem_u32)
 __device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool toward_high)
 {
-    if (r < kLrRows) return lds_u32(lr + 4u * r);
+    if (r < kLrRows) return lds_u32(lr + 4u * lr_slot(r));
     const uint32_t o = slow_row(r, toward_high);
     return o | (o << 16);
 }
@@ -235,25 +363,30 @@ __device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool towa
 // GUARD = false skips the range test: only for callers that can PROVE every row is in the table
 // (the rollout kernel: a board whose tiles sum to less than 16384 has no 16384 tile).
 template <bool GUARD = true>
-__device__ __forceinline__ void move_lr(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t lr)
+__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, bool toward_high, uint32_t lr,
+                                        const PipeConsts &pc)
 {
-    const bool vertical = action < 2u;
-    const bool toward_high = (action & 1u) != 0u;      // DOWN or RIGHT
-    if (vertical) transpose(lo, hi);
-    const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
     uint32_t o0, o1, o2, o3;
-    if (!GUARD || __builtin_expect((r0 | r1 | r2 | r3) < kLrRows, 1)) {   // OR >= any row: conservative
-        o0 = lds_u32(lr + 4u * r0); o1 = lds_u32(lr + 4u * r1);
-        o2 = lds_u32(lr + 4u * r2); o3 = lds_u32(lr + 4u * r3);
+    // a row is outside the table iff its top three bits are set; OR-ing the words first is a
+    // conservative test (it may send a board to the exact path for nothing)
+    const uint32_t both = lo | hi;
+    if (!GUARD || __builtin_expect((both & (both << 1) & (both << 2) & 0x80008000u) == 0u, 1)) {
+        uint32_t a0, a1, a2, a3;
+        row_offsets(lo, pc, a0, a1);
+        row_offsets(hi, pc, a2, a3);
+        o0 = lds_u32(lr + a0); o1 = lds_u32(lr + a1);
+        o2 = lds_u32(lr + a2); o3 = lds_u32(lr + a3);
     } else {
+        const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
         o0 = lr_lookup(lr, r0, toward_high); o1 = lr_lookup(lr, r1, toward_high);
         o2 = lr_lookup(lr, r2, toward_high); o3 = lr_lookup(lr, r3, toward_high);
     }
     const uint32_t pk = toward_high ? 0x7632u : 0x5410u;
     lo = prmt(o0, o1, pk);
     hi = prmt(o2, o3, pk);
-    if (vertical) transpose(lo, hi);
 }
+
+// Game.update_matrix on a board in its true orientation (transposes inside)
 
 // all four afterstates: LEFT/RIGHT share one lookup per row, UP/DOWN one per column
 template <bool GUARD = true>
@@ -270,11 +403,11 @@ __device__ __forceinline__ void move_all(uint32_t lo, uint32_t hi, uint32_t lr,
     for (int t = 0; t < 8; t++) any |= r[t];
     if (!GUARD || __builtin_expect(any < kLrRows, 1)) {
 #pragma unroll
-        for (int t = 0; t < 8; t++) o[t] = lds_u32(lr + 4u * r[t]);
+        for (int t = 0; t < 8; t++) o[t] = lds_u32(lr + 4u * lr_slot(r[t]));
     } else {
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            if (r[t] < kLrRows) o[t] = lds_u32(lr + 4u * r[t]);
+            if (r[t] < kLrRows) o[t] = lds_u32(lr + 4u * lr_slot(r[t]));
             else o[t] = slow_row(r[t], false) | (slow_row(r[t], true) << 16);
         }
     }
@@ -318,7 +451,8 @@ __device__ __forceinline__ Blanks count_blanks(uint32_t lo, uint32_t hi)
     return b;
 }
 
-// one-hot (bit 3 of the chosen nibble) mask of the k-th blank; zero if k >= n
+// one-hot (bit 3 of the chosen nibble) mask of the k-th blank; zero if n <= k <= 15 (k * 0x11111111
+// wraps for k >= 16: callers that take k from outside use place_tile_checked)
 __device__ __forceinline__ void kth_blank(const Blanks &b, uint32_t k, uint32_t &sl, uint32_t &sh)
 {
     const uint32_t kk = k * 0x11111111u;
@@ -337,6 +471,13 @@ __device__ __forceinline__ void place_tile(uint32_t &lo, uint32_t &hi, const Bla
     kth_blank(b, k, sl, sh);
     lo += (sl >> 3) * vexp;
     hi += (sh >> 3) * vexp;
+}
+
+// k from the caller (injected draws): any k >= n leaves the board as it is
+__device__ __forceinline__ void place_tile_checked(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
+                                                   uint32_t vexp)
+{
+    place_tile(lo, hi, b, k & 15u, k < b.n ? vexp : 0u);
 }
 
 // The same for vexp in {0,1,2} given as v29 = vexp << 29: the high half of

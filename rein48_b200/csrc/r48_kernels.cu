@@ -11,13 +11,15 @@
 //   afterstates_kernel    4 x Game.update_matrix + over    GameClient.py:129-254, 65-94
 //   rollout_kernel        main.play(control="rand")        main.py:36-42 + rand.py:9-11
 //                         <policy, record>: random | greedy-blanks; play | replay-and-record
-//   stats/scores/decode/encode  readout                     main.py:48, a3c.py:195,205
+//   stats/scores/records/decode/encode  readout             main.py:48, a3c.py:195,205
+//   ring_append/ring_sample  Replay.store / Replay.sample   algorithm/ddpg/replay.py:8-47
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
 #include <type_traits>
+#include <new>
 
 #include "../../include/r48.h"
 #include "r48_device.cuh"
@@ -70,7 +72,7 @@ __global__ void build_tables_kernel(uint16_t *left, uint8_t *merges, uint32_t *l
         left[r] = (uint16_t)l;
         merges[r] = (uint8_t)m;
         // RIGHT on r = mirror image of LEFT on the mirrored row
-        if (r < kLrRows) lr[r] = l | (reverse_row(slow_row_left(reverse_row(r), m)) << 16);
+        if (r < kLrRows) lr[lr_slot(r)] = l | (reverse_row(slow_row_left(reverse_row(r), m)) << 16);
     }
 }
 
@@ -80,6 +82,7 @@ struct Tables {
     const uint16_t *left;        // 65536 x u16
     const uint8_t *merges;       // 65536 x u8
     const uint32_t *lr;          // kLrRows x u32
+    PipeConsts pc;
 };
 
 // REWARD: [left u16 x 65536][merges u8 x 65536] (192 KB); otherwise [lr u32 x kLrRows] (224 KB)
@@ -122,15 +125,23 @@ struct ResetParams {
     PhiloxKeys keys;
 };
 
+// Game.reset: the tick-0 draw on the empty board.  The word's own action field names the axis
+// whose order counts the blanks, exactly as the fused rollout does at tick 0.
+__device__ __forceinline__ void reset_board(uint32_t &lo, uint32_t &hi, uint32_t a)
+{
+    lo = 0u; hi = 0u;
+    const Blanks b = count_blanks(lo, hi);
+    place_tile(lo, hi, b, __umulhi(a << 2, b.n), spawn_exp(a));
+    if (is_vertical(a >> 30)) transpose(lo, hi);
+}
+
 __global__ void __launch_bounds__(256) reset_kernel(ResetParams p)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t a, v;
-        draw_words(p.board_base + (uint64_t)i, 0u, p.keys, a, v);
-        uint32_t lo = 0, hi = 0;
-        Blanks b = count_blanks(lo, hi);
-        place_tile(lo, hi, b, __umulhi(a << 2, b.n), v < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+        const uint32_t a = draw_word(p.board_base + (uint64_t)i, 0u, p.keys);
+        uint32_t lo, hi;
+        reset_board(lo, hi, a);
         p.boards[i] = ((uint64_t)hi << 32) | lo;
     }
 }
@@ -143,21 +154,21 @@ __global__ void __launch_bounds__(256) spawn_injected_kernel(uint64_t *boards, c
         const uint64_t b = boards[i];
         uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
         const Blanks bl = count_blanks(lo, hi);
-        place_tile(lo, hi, bl, spawn_k[i], spawn_exp[i] & 15u);
+        place_tile_checked(lo, hi, bl, spawn_k[i], spawn_exp[i] & 15u);
         boards[i] = ((uint64_t)hi << 32) | lo;
     }
 }
 
+// Game.random_fill_grid alone, GPU draws, blanks counted row-major (no move, hence no axis)
 __global__ void __launch_bounds__(256) spawn_kernel(ResetParams p, uint32_t tick)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t a, v;
-        draw_words(p.board_base + (uint64_t)i, tick, p.keys, a, v);
+        const uint32_t a = draw_word(p.board_base + (uint64_t)i, tick, p.keys);
         const uint64_t b = p.boards[i];
         uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
         const Blanks bl = count_blanks(lo, hi);
-        place_tile(lo, hi, bl, __umulhi(a << 2, bl.n), v < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+        place_tile(lo, hi, bl, __umulhi(a << 2, bl.n), spawn_exp(a));
         p.boards[i] = ((uint64_t)hi << 32) | lo;
     }
 }
@@ -183,45 +194,71 @@ struct StepParams {
     int32_t *reward;             // may be NULL
     uint8_t *done;               // may be NULL
     int32_t *status;             // may be NULL
-    int64_t n;
-    uint64_t board_base;
-    uint32_t tick;               // step + 1
+    uint32_t n;                  // boards of this launch (the host splits at 2^30 boards ...
+    uint32_t id_lo;              // ... and at multiples of 2^32 ids: id.hi is a launch constant)
+    PhiloxLaunch pl;
     PhiloxKeys keys;
     Tables tables;
 };
 
-// One board through Game.step.  No branches on the data: an illegal action byte (> 3) is
-// flagged and the board passed through by selects (GameClient.py:254 raises there).
+// One board through Game.step.  `aw` = the tick's Philox word (or the injected k), `vw` = the
+// injected exponent.  An action byte > 3 (GameClient.py:254 raises there) sets `bad` and passes
+// the board through.
+//
+// The spawn counts blanks in the order of the move's axis, so for UP/DOWN it happens on the
+// transposed board, between the two transposes (nothing extra to compute); injected draws index
+// the reference's row-major blank list (GameClient.py:109-114), so there the board is transposed
+// back first.  has_game_over is symmetric under transposition and is evaluated wherever the board
+// happens to be, and only for boards that are full after the spawn.
 template <bool REWARD, bool INJECT>
 __device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
-                                         uint32_t vw, const uint8_t *smem, uint32_t lr, int32_t &reward,
-                                         uint32_t &done, uint32_t &bad)
+                                         uint32_t vw, const uint8_t *smem, uint32_t lr, const PipeConsts &pc,
+                                         int32_t &reward, uint32_t &done, uint32_t &bad)
 {
+    const uint32_t in_lo = lo, in_hi = hi;
+    const bool vertical = is_vertical(action);
+    if (vertical) transpose(lo, hi);
     const uint32_t olo = lo, ohi = hi;
-    const bool legal = action <= 3u;
-    bad |= legal ? 0u : 1u;
     uint32_t rw = 0;
-    if (REWARD) move_l16<true>(lo, hi, action, (const uint16_t *)smem, smem + kLeftBytes, rw);
-    else move_lr(lo, hi, action, lr);
-    if (!legal) { lo = olo; hi = ohi; rw = 0; }
+    if (REWARD) rows_l16<true>(lo, hi, is_toward_high(action), (const uint16_t *)smem, smem + kLeftBytes, rw);
+    else rows_lr(lo, hi, is_toward_high(action), lr, pc);
     const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
-    const Blanks b = count_blanks(lo, hi);
+    bool full;
     if (INJECT) {
-        place_tile(lo, hi, b, aw, changed ? (vw & 15u) : 0u);
+        if (vertical) transpose(lo, hi);
+        const Blanks b = count_blanks(lo, hi);
+        place_tile_checked(lo, hi, b, aw, changed ? (vw & 15u) : 0u);
+        full = (any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u;
     } else {
-        const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
-        place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), v29);
+        const Blanks b = count_blanks(lo, hi);
+        place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), spawn_v29(aw, changed));
+        // full after the spawn <=> the moved board had no blank, or exactly one that was filled
+        full = b.n == (changed ? 1u : 0u);
     }
-    // full after the spawn <=> the moved board had no blank, or exactly one that was filled
-    const bool full = INJECT ? ((any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u)
-                             : (b.n == (changed ? 1u : 0u));
-    done = (full && no_equal_neighbours(lo, hi)) ? 1u : 0u;
+    done = 0u;
+    if (full) done = no_equal_neighbours(lo, hi) ? 1u : 0u;
+    if (!INJECT && vertical) transpose(lo, hi);
     reward = REWARD ? (int32_t)rw : 0;
+    if (__builtin_expect(action > 3u, 0)) {
+        bad = 1u;
+        lo = in_lo; hi = in_hi; reward = 0;
+        done = game_over(lo, hi) ? 1u : 0u;
+    }
 }
 
-// VEC: two boards per thread per trip with 128-bit board loads/stores (needs 16-byte aligned
-// in/out, 8-byte reward, 2-byte action/done); otherwise one board per thread per trip.  The
-// trip loop carries no data-dependent branch, so the two boards of a pair interleave.
+// Work split: every CTA owns one contiguous slice of the batch (equal slices, so all SMs finish
+// together even when a launch is only a few trips long -- 2^20 boards are 7 boards per thread),
+// and walks it in warp chunks: lane L takes units L and 32+L of a 64-unit chunk, both loads are
+// issued before any compute and the chunk of the NEXT trip is prefetched into L2 at the same
+// time, so that its loads find the data there instead of waiting on HBM.  Short slices (small
+// launches) use 32-unit chunks, one unit per lane, to spread over more warps.  VEC: a unit is a
+// PAIR of boards moved with 128-bit loads/stores (needs 16-byte aligned in/out, 8-byte reward,
+// 2-byte action/done), i.e. up to four boards per thread per trip; otherwise a unit is one board.
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <bool REWARD, bool INJECT, bool VEC>
 __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
 {
@@ -232,69 +269,141 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
 
     bool ready = false;
     uint32_t bad = 0;
-    // 32-bit indices (the host splits batches of 2^30 boards and more): every array address is
-    // one IMAD.WIDE from the index
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = (uint32_t)p.n;
-    const bool odd = (p.tick & 1u) != 0u;
-    const uint32_t pairs = VEC ? (n >> 1) : 0u;
-    if (VEC)
-    for (uint32_t j = tid; j < pairs; j += stride) {
-        const ulonglong2 bb = ((const ulonglong2 *)p.in)[j];
-        const uchar2 aa = ((const uchar2 *)p.action)[j];
-        uint32_t k0, k1, v0, v1;
-        if (INJECT) {
-            const uchar2 kk = ((const uchar2 *)p.spawn_k)[j];
-            const uchar2 vv = ((const uchar2 *)p.spawn_exp)[j];
-            k0 = kk.x; k1 = kk.y; v0 = vv.x; v1 = vv.y;
+    const uint32_t units = VEC ? (p.n >> 1) : p.n;
+    const uint32_t per = ((units + gridDim.x - 1u) / gridDim.x + 31u) & ~31u;
+    const uint32_t begin = min(units, blockIdx.x * per), end = min(units, begin + per);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool dual = per > (uint32_t)kThreads;          // CTA-uniform: two units per lane per trip
+    const uint32_t chunk = dual ? 64u : 32u, trip = (kThreads / 32) * chunk;
+
+    auto draw = [&](uint32_t board) -> uint32_t {          // the tick's word for board index `board`
+        return philox_launch_word(p.id_lo + board, p.pl, p.keys);
+    };
+
+    for (uint32_t u0 = begin + warp * chunk + lane; u0 < end; u0 += trip) {
+        const uint32_t u1 = u0 + 32u;
+        const bool two = dual && u1 < end;
+        if (VEC) {
+            ulonglong2 b0 = ((const ulonglong2 *)p.in)[u0], b1 = make_ulonglong2(0ull, 0ull);
+            uchar2 a0 = ((const uchar2 *)p.action)[u0], a1 = make_uchar2(0, 0);
+            if (two) { b1 = ((const ulonglong2 *)p.in)[u1]; a1 = ((const uchar2 *)p.action)[u1]; }
+            if (u0 + trip < end) {
+                prefetch_l2((const ulonglong2 *)p.in + u0 + trip);
+                if (dual && u1 + trip < end) prefetch_l2((const ulonglong2 *)p.in + u1 + trip);
+                if ((lane & 15u) == 0u) prefetch_l2((const uchar2 *)p.action + u0 + trip);    // 32 B sectors
+                if (dual && (lane & 15u) == 0u && u1 + trip < end) prefetch_l2((const uchar2 *)p.action + u1 + trip);
+            }
+            uint32_t k[4], v[4] = {0u, 0u, 0u, 0u};
+            if (INJECT) {
+                const uchar2 kk = ((const uchar2 *)p.spawn_k)[u0], vv = ((const uchar2 *)p.spawn_exp)[u0];
+                k[0] = kk.x; k[1] = kk.y; v[0] = vv.x; v[1] = vv.y; k[2] = k[3] = 0u;
+                if (two) {
+                    const uchar2 kk1 = ((const uchar2 *)p.spawn_k)[u1], vv1 = ((const uchar2 *)p.spawn_exp)[u1];
+                    k[2] = kk1.x; k[3] = kk1.y; v[2] = vv1.x; v[3] = vv1.y;
+                }
+            } else {
+                k[0] = draw(2u * u0); k[1] = draw(2u * u0 + 1u);
+                k[2] = k[3] = 0u;
+                if (two) { k[2] = draw(2u * u1); k[3] = draw(2u * u1 + 1u); }
+            }
+            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            uint32_t lo[4] = {(uint32_t)b0.x, (uint32_t)b0.y, (uint32_t)b1.x, (uint32_t)b1.y};
+            uint32_t hi[4] = {(uint32_t)(b0.x >> 32), (uint32_t)(b0.y >> 32), (uint32_t)(b1.x >> 32), (uint32_t)(b1.y >> 32)};
+            const uint32_t act[4] = {a0.x, a0.y, a1.x, a1.y};
+            int32_t r[4] = {0, 0, 0, 0};
+            uint32_t d[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int t = 0; t < 2; t++) step_one<REWARD, INJECT>(lo[t], hi[t], act[t], k[t], v[t], smem, lr, p.tables.pc, r[t], d[t], bad);
+            ((ulonglong2 *)p.out)[u0] = make_ulonglong2(((uint64_t)hi[0] << 32) | lo[0], ((uint64_t)hi[1] << 32) | lo[1]);
+            if (p.reward) ((int2 *)p.reward)[u0] = make_int2(r[0], r[1]);
+            if (p.done) ((uchar2 *)p.done)[u0] = make_uchar2((uint8_t)d[0], (uint8_t)d[1]);
+            if (two) {
+#pragma unroll
+                for (int t = 2; t < 4; t++) step_one<REWARD, INJECT>(lo[t], hi[t], act[t], k[t], v[t], smem, lr, p.tables.pc, r[t], d[t], bad);
+                ((ulonglong2 *)p.out)[u1] = make_ulonglong2(((uint64_t)hi[2] << 32) | lo[2], ((uint64_t)hi[3] << 32) | lo[3]);
+                if (p.reward) ((int2 *)p.reward)[u1] = make_int2(r[2], r[3]);
+                if (p.done) ((uchar2 *)p.done)[u1] = make_uchar2((uint8_t)d[2], (uint8_t)d[3]);
+            }
         } else {
-            uint32_t w[4];
-            const uint64_t id0 = p.board_base + 2ull * j;
-            philox4x32_10((uint32_t)id0, (uint32_t)(id0 >> 32), p.tick >> 1, 0u, p.keys, w);
-            k0 = odd ? w[2] : w[0]; v0 = odd ? w[3] : w[1];
-            const uint64_t id1 = id0 + 1;
-            philox4x32_10((uint32_t)id1, (uint32_t)(id1 >> 32), p.tick >> 1, 0u, p.keys, w);
-            k1 = odd ? w[2] : w[0]; v1 = odd ? w[3] : w[1];
+            uint64_t b0 = p.in[u0], b1 = 0ull;
+            uint32_t act[2] = {p.action[u0], 0u};
+            if (two) { b1 = p.in[u1]; act[1] = p.action[u1]; }
+            uint32_t k[2], v[2] = {0u, 0u};
+            if (INJECT) {
+                k[0] = p.spawn_k[u0]; v[0] = p.spawn_exp[u0]; k[1] = 0u;
+                if (two) { k[1] = p.spawn_k[u1]; v[1] = p.spawn_exp[u1]; }
+            } else {
+                k[0] = draw(u0); k[1] = two ? draw(u1) : 0u;
+            }
+            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            uint32_t lo[2] = {(uint32_t)b0, (uint32_t)b1}, hi[2] = {(uint32_t)(b0 >> 32), (uint32_t)(b1 >> 32)};
+            int32_t r[2] = {0, 0};
+            uint32_t d[2] = {0u, 0u};
+            step_one<REWARD, INJECT>(lo[0], hi[0], act[0], k[0], v[0], smem, lr, p.tables.pc, r[0], d[0], bad);
+            p.out[u0] = ((uint64_t)hi[0] << 32) | lo[0];
+            if (p.reward) p.reward[u0] = r[0];
+            if (p.done) p.done[u0] = (uint8_t)d[0];
+            if (two) {
+                step_one<REWARD, INJECT>(lo[1], hi[1], act[1], k[1], v[1], smem, lr, p.tables.pc, r[1], d[1], bad);
+                p.out[u1] = ((uint64_t)hi[1] << 32) | lo[1];
+                if (p.reward) p.reward[u1] = r[1];
+                if (p.done) p.done[u1] = (uint8_t)d[1];
+            }
         }
-        if (!ready) { mbar_wait(&bar, 0); ready = true; }
-        uint32_t lo0 = (uint32_t)bb.x, hi0 = (uint32_t)(bb.x >> 32);
-        uint32_t lo1 = (uint32_t)bb.y, hi1 = (uint32_t)(bb.y >> 32);
-        int32_t r0, r1;
-        uint32_t d0, d1;
-        step_one<REWARD, INJECT>(lo0, hi0, aa.x, k0, v0, smem, lr, r0, d0, bad);
-        step_one<REWARD, INJECT>(lo1, hi1, aa.y, k1, v1, smem, lr, r1, d1, bad);
-        ((ulonglong2 *)p.out)[j] = make_ulonglong2(((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
-        if (p.reward) ((int2 *)p.reward)[j] = make_int2(r0, r1);
-        if (p.done) ((uchar2 *)p.done)[j] = make_uchar2((uint8_t)d0, (uint8_t)d1);
     }
-    // boards not covered by pairs: everything (scalar kernel) or the odd last one
-    for (uint32_t i = 2u * pairs + tid; i < n; i += stride) {
+    // the odd last board of a vectorised launch
+    if (VEC && (p.n & 1u) && blockIdx.x == gridDim.x - 1u && threadIdx.x == 0u) {
+        const uint32_t i = p.n - 1u;
         const uint64_t b0 = p.in[i];
-        const uint32_t a0 = p.action[i];
-        uint32_t k0, v0;
-        if (INJECT) {
-            k0 = p.spawn_k[i];
-            v0 = p.spawn_exp[i];
-        } else {
-            uint32_t w[4];
-            const uint64_t id0 = p.board_base + (uint64_t)i;
-            philox4x32_10((uint32_t)id0, (uint32_t)(id0 >> 32), p.tick >> 1, 0u, p.keys, w);
-            k0 = odd ? w[2] : w[0]; v0 = odd ? w[3] : w[1];
-        }
+        uint32_t lo = (uint32_t)b0, hi = (uint32_t)(b0 >> 32), d;
+        int32_t r;
+        const uint32_t k = INJECT ? (uint32_t)p.spawn_k[i] : draw(i);
+        const uint32_t v = INJECT ? (uint32_t)p.spawn_exp[i] : 0u;
         if (!ready) { mbar_wait(&bar, 0); ready = true; }
-        uint32_t lo0 = (uint32_t)b0, hi0 = (uint32_t)(b0 >> 32), d0;
-        int32_t r0;
-        step_one<REWARD, INJECT>(lo0, hi0, a0, k0, v0, smem, lr, r0, d0, bad);
-        p.out[i] = ((uint64_t)hi0 << 32) | lo0;
-        if (p.reward) p.reward[i] = r0;
-        if (p.done) p.done[i] = (uint8_t)d0;
+        step_one<REWARD, INJECT>(lo, hi, p.action[i], k, v, smem, lr, p.tables.pc, r, d, bad);
+        p.out[i] = ((uint64_t)hi << 32) | lo;
+        if (p.reward) p.reward[i] = r;
+        if (p.done) p.done[i] = (uint8_t)d;
     }
     if (bad && p.status) atomicOr(p.status, 1);
     if (!ready) mbar_wait(&bar, 0);          // never leave with the bulk copy in flight
 }
 
 // ------------------------------------------------------------------ vectorised env step
+
+// Optional transition ring (SoA; see r48_ring_append): slot (cursor[0] + i) % capacity receives
+// the transition of env i; the last CTA to finish adds n to cursor[0].
+struct RingRefs {
+    uint64_t *state;
+    uint8_t *action;
+    int32_t *reward;
+    uint64_t *next_state;
+    uint8_t *done;
+    uint64_t *cursor;            // [0] transitions appended so far, [1] CTA ticket (zero between launches)
+    uint64_t capacity;
+};
+
+// first slot of an append of n (<= capacity unless `skip` says otherwise) transitions and the
+// number of leading items that a later item of the same append would overwrite anyway
+__device__ __forceinline__ uint64_t ring_start(const RingRefs &r, uint64_t n, uint64_t &skip)
+{
+    skip = n > r.capacity ? n - r.capacity : 0ull;
+    return (r.cursor[0] + skip) % r.capacity;
+}
+
+__device__ __forceinline__ void ring_finish(const RingRefs &r, uint64_t n)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd((unsigned long long *)&r.cursor[1], 1ull);
+        if (t == gridDim.x - 1u) {
+            r.cursor[0] += n;
+            r.cursor[1] = 0ull;
+            __threadfence();
+        }
+    }
+}
 
 struct EnvParams {
     uint64_t *boards;
@@ -313,10 +422,12 @@ struct EnvParams {
     int auto_reset;
     PhiloxKeys keys;
     Tables tables;
+    RingRefs ring;               // ring.state == NULL: no ring
 };
 
-// Game.step with per-env tick / episode counters, optional auto-reset and the float readout
-// fused into the epilogue (one pass over the board instead of step + decode).
+// Game.step with per-env tick / episode counters, optional auto-reset, the float readout and the
+// replay-ring append fused into the epilogue (one pass over the board instead of step + decode +
+// append).
 template <bool REWARD>
 __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
 {
@@ -329,6 +440,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     uint32_t bad = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
+    uint64_t ring_skip = 0, ring_at = 0;
+    if (p.ring.state) ring_at = ring_start(p.ring, p.n, ring_skip);
     // warp-uniform trip count: the readout below shuffles boards between the lanes of a warp
     for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < p.n; base += stride) {
         const uint32_t i = base + lane;
@@ -339,22 +452,28 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
             const uint32_t a = p.action[i];
             uint32_t st = p.steps[i], ep = p.episodes[i];
             uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
-            uint32_t aw, vw;
-            draw_words(id, st + 1u, p.keys, aw, vw);
+            uint32_t aw = draw_word(id, st + 1u, p.keys);
             if (!ready) { mbar_wait(&bar, 0); ready = true; }
             lo = (uint32_t)b; hi = (uint32_t)(b >> 32);
             uint32_t d;
             int32_t r;
-            step_one<REWARD, false>(lo, hi, a, aw, vw, smem, lr, r, d, bad);
+            step_one<REWARD, false>(lo, hi, a, aw, 0u, smem, lr, p.tables.pc, r, d, bad);
             st += 1u;
+            if (p.ring.state && i >= ring_skip) {
+                uint64_t slot = ring_at + (i - ring_skip);
+                if (slot >= p.ring.capacity) slot -= p.ring.capacity;
+                p.ring.state[slot] = b;
+                p.ring.action[slot] = (uint8_t)a;
+                p.ring.reward[slot] = r;
+                p.ring.next_state[slot] = ((uint64_t)hi << 32) | lo;      // the board the step produced,
+                p.ring.done[slot] = (uint8_t)d;                            // not the auto-reset one
+            }
             if (d && p.auto_reset) {                 // rare: a lane's game ended
                 if (p.final_boards) p.final_boards[i] = ((uint64_t)hi << 32) | lo;
                 ep += 1u; st = 0u;
                 id = p.board_base + i + (uint64_t)ep * p.id_stride;
-                draw_words(id, 0u, p.keys, aw, vw);
-                lo = 0u; hi = 0u;
-                const Blanks bl = count_blanks(lo, hi);
-                place_tile(lo, hi, bl, __umulhi(aw << 2, bl.n), vw < R48_SPAWN4_THRESHOLD ? 2u : 1u);
+                aw = draw_word(id, 0u, p.keys);
+                reset_board(lo, hi, aw);
             }
             p.boards[i] = ((uint64_t)hi << 32) | lo;
             p.steps[i] = st;
@@ -386,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     }
     if (bad && p.status) atomicOr(p.status, 1);
     if (!ready) mbar_wait(&bar, 0);
+    if (p.ring.state) ring_finish(p.ring, p.n);
 }
 
 // ------------------------------------------------------------------ afterstates
@@ -422,7 +542,9 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
 #pragma unroll
             for (uint32_t a = 0; a < 4; a++) {
                 uint32_t l = lo, h = hi;
-                move_l16<true>(l, h, a, (const uint16_t *)smem, smem + kLeftBytes, rw[a]);
+                if (is_vertical(a)) transpose(l, h);
+                rows_l16<true>(l, h, is_toward_high(a), (const uint16_t *)smem, smem + kLeftBytes, rw[a]);
+                if (is_vertical(a)) transpose(l, h);
                 if ((l ^ lo) | (h ^ hi)) mask |= 1u << a;
                 res[a] = ((uint64_t)h << 32) | l;
             }
@@ -453,7 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
 struct RolloutParams {
     uint64_t *final_boards;
     uint32_t *lengths;
-    unsigned int *counter;           // next unassigned episode (32-bit: the host splits launches)
+    unsigned int *counter;           // next unassigned block of episodes (32-bit: the host splits launches)
     uint32_t n;
     uint64_t board_base;
     PhiloxKeys keys;
@@ -464,10 +586,17 @@ struct RolloutParams {
     uint8_t *traj_actions;           // the action taken at that step
 };
 
-// One lane = one episode at a time, board in two registers; when its game ends the lane
-// takes the next episode index from a global counter (legal because every draw is keyed by
-// the episode's GLOBAL id and tick, not by the lane that plays it), so warps stay full
-// until the queue is empty.  One Philox call feeds two consecutive ticks.
+// One lane = one episode at a time, board in two registers; when its game ends the lane takes the
+// next episode index (legal because every draw is keyed by the episode's GLOBAL id and tick, not
+// by the lane that plays it), so warps stay full until the queue is empty.  A warp draws indices
+// from a private block of 32 that it refills with one atomic on the global counter: the common
+// switch costs no atomic and no memory round trip.  One Philox call feeds four consecutive ticks.
+//
+// Orientation is lazy.  The board is kept transposed after an UP/DOWN move and straight after a
+// LEFT/RIGHT one (the spawn counts blanks in the order of the move's axis, so it runs on the
+// board as stored); a tick transposes only when its axis differs from the previous tick's --
+// one 10-instruction transpose on half the ticks instead of two on half the ticks.  The final
+// board is put straight before it is written.
 //
 // Game over is detected lazily: has_game_over (GameClient.py:65-94) holds exactly when no
 // move changes the board, and on a FULL board a horizontal move fails iff no two
@@ -477,6 +606,7 @@ struct RolloutParams {
 // length.  This replaces a ~20-instruction neighbour test per tick by a few predicated ops
 // at the price of ~3 extra no-op ticks per episode (2 %); outputs are identical.
 enum : int { kPolicyRandom = 0, kPolicyGreedyBlanks = 1 };
+constexpr uint32_t kEpisodeBlock = 32;      // episode indices a warp takes per atomic
 
 // number of blank cells of a board (selection only; the spawn uses count_blanks)
 __device__ __forceinline__ uint32_t blank_count(uint32_t lo, uint32_t hi)
@@ -496,13 +626,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     stage_tables<false>(smem, p.tables, &bar);
 
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     // random policy: `failed` collects the axes seen to fail on the current full board (3 = over);
     // greedy policy: `failed` is simply set to 3 when no move changes the board
     uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
+    uint32_t axis_word = 0x80000000u;       // sign bit clear <=> the board is stored transposed
     uint32_t ep = kNone;
     PhiloxEpisode pe = {0u, 0u, 0u};        // per-episode part of the Philox call
-    uint32_t id_lo = 0, id_hi = 0;
+    uint32_t id_hi = 0;
+    uint32_t blk_next = 0, blk_end = 0;     // warp-uniform: the warp's private block of episode indices
     uint32_t rec_len = 0;       // RECORD: length of the episode being replayed ...
     uint64_t rec_off = 0;       // ... and its first output slot (a multiple of 4)
     // RECORD: four steps are gathered in registers and leave as one full 32-byte sector (two
@@ -516,90 +649,129 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         const bool fin = live && failed == 3u;          // episode over
         if (__any_sync(kFull, fin)) {
             if (!RECORD && fin && ep != kNone) {
+                if ((int32_t)axis_word >= 0) transpose(lo, hi);
                 p.final_boards[ep] = ((uint64_t)hi << 32) | lo;
                 p.lengths[ep] = last_change;
             }
             const uint32_t want = __ballot_sync(kFull, fin);
-            const uint32_t leader = __ffs(want) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(p.counter, (unsigned int)__popc(want));
-            base = __shfl_sync(kFull, base, leader);
+            const uint32_t cnt = __popc(want), rem = blk_end - blk_next;
+            uint32_t fresh = 0;
+            if (cnt > rem) {                            // warp-uniform: the private block runs out
+                if (lane == 0) fresh = atomicAdd(p.counter, kEpisodeBlock);
+                fresh = __shfl_sync(kFull, fresh, 0);
+            }
             if (fin) {
-                const uint32_t mine = base + __popc(want & ((1u << lane) - 1u));
+                const uint32_t rank = __popc(want & lanes_below);
+                const uint32_t mine = rank < rem ? blk_next + rank : fresh + (rank - rem);
                 if (mine < p.n) {
-                    ep = mine; lo = 0; hi = 0; tick = 0; failed = 0;
+                    ep = mine; lo = 0; hi = 0; tick = 0; failed = 0; axis_word = 0x80000000u;
                     const uint64_t id = p.board_base + mine;
-                    id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32);
-                    pe = philox_episode(id_lo, p.keys);
+                    id_hi = (uint32_t)(id >> 32);
+                    pe = philox_episode((uint32_t)id, p.keys);
                     if (RECORD) { rec_len = p.lengths[mine]; rec_off = p.traj_offsets[mine]; }
                 } else {                       // queue empty: park on the empty board (failed stays 3)
                     live = false; ep = kNone; rec_len = 0;
                     lo = 0; hi = 0; tick = 2;
                 }
             }
+            if (cnt > rem) { blk_next = fresh + (cnt - rem); blk_end = fresh + kEpisodeBlock; }
+            else blk_next += cnt;
             if (!__any_sync(kFull, live)) break;
         }
 
         uint32_t w[4];
-        philox4x32_10_episode(id_lo, id_hi, tick >> 1, pe, p.keys, w);
+        philox4x32_episode(id_hi, tick >> 2, pe, p.keys, w);
 
         // The tiles of a board sum to at most 4 per spawn, so before tick 4000 no tile can be
-        // 16384 and every row is inside the LR table: the range test of move_lr is provably
-        // dead.  One warp vote per pair of ticks selects the unguarded body (always, in
+        // 16384 and every row is inside the LR table: the range test of rows_lr is provably
+        // dead.  One warp vote per four ticks selects the unguarded body (always, in
         // practice: random games last a few hundred ticks); the guarded one stays for the rest.
-        auto two_ticks = [&](auto guard_tag) {
+        auto four_ticks = [&](auto guard_tag) {
             constexpr bool kGuard = decltype(guard_tag)::value;
 #pragma unroll
-            for (int half_i = 0; half_i < 2; half_i++) {
-                const int half = half_i;
-                const uint32_t aw = w[2 * half], vw = w[2 * half + 1];
-                const uint32_t olo = lo, ohi = hi;
+            for (int j = 0; j < 4; j++) {
+                const uint32_t aw = w[j];
                 uint32_t taken = aw >> 30;
                 bool changed;
+                uint32_t rec_b_lo = 0, rec_b_hi = 0;        // RECORD: the board before the step, straight
                 if (POLICY == kPolicyRandom) {
-                    move_lr<kGuard>(lo, hi, aw >> 30, lr);
-                    // tick 0 is the reset spawn on the empty board (GameClient.py:33-38)
-                    changed = (((lo ^ olo) | (hi ^ ohi)) != 0u) || (tick == 0u);
+                    if ((int32_t)(aw ^ axis_word) < 0) transpose(lo, hi);       // the axis changes
+                    axis_word = aw;
+                    if (RECORD) { rec_b_lo = lo; rec_b_hi = hi; if ((int32_t)aw >= 0) transpose(rec_b_lo, rec_b_hi); }
+                    const uint32_t olo = lo, ohi = hi;
+                    rows_lr<kGuard>(lo, hi, (aw & 0x40000000u) != 0u, lr, p.tables.pc);
+                    changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
+                    // tick 0 is the reset spawn on the empty board (GameClient.py:33-38); an episode
+                    // starts at the top of an iteration, so only j == 0 can be it
+                    if (j == 0) changed = changed || (tick == 0u);
                 } else {
-                    // all four afterstates; key = blanks * 4 + (3 - rotation offset), -1 if the move
-                    // changes nothing: the maximum is the greedy choice with the first-best tie rule
-                    uint32_t rl[4], rh[4];
-                    move_all<kGuard>(lo, hi, lr, rl, rh);
-                    const uint32_t r = aw >> 30;
-                    int best = -1;
-                    uint32_t bl = lo, bh = hi;
+                    // All four afterstates: the rows of the stored board give one axis, the rows of
+                    // its transpose the other; a candidate stays in the orientation it was computed
+                    // in.  key = blanks * 4 + (3 - rotation offset), -1 if the move changes nothing:
+                    // the maximum is the greedy choice with the first-best tie rule.
+                    if (j == 0 && tick == 0u) axis_word = aw;                   // the reset draw names its axis
+                    const bool stored_t = (int32_t)axis_word >= 0;
+                    uint32_t yl = lo, yh = hi;
+                    transpose(yl, yh);
+                    if (RECORD) { rec_b_lo = stored_t ? yl : lo; rec_b_hi = stored_t ? yh : hi; }
+                    const uint32_t r[8] = {lo & 0xFFFFu, lo >> 16, hi & 0xFFFFu, hi >> 16,
+                                           yl & 0xFFFFu, yl >> 16, yh & 0xFFFFu, yh >> 16};
+                    uint32_t o[8];
+                    if (kGuard) {
 #pragma unroll
-                    for (uint32_t a = 0; a < 4; a++) {
-                        const bool valid = ((rl[a] ^ lo) | (rh[a] ^ hi)) != 0u;
-                        const int key = valid ? (int)(blank_count(rl[a], rh[a]) * 4u + (3u - ((a - r) & 3u))) : -1;
-                        if (key > best) { best = key; bl = rl[a]; bh = rh[a]; taken = a; }
+                        for (int t = 0; t < 8; t++) {
+                            if (r[t] < kLrRows) o[t] = lds_u32(lr + 4u * lr_slot(r[t]));
+                            else o[t] = slow_row(r[t], false) | (slow_row(r[t], true) << 16);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 8; t++) o[t] = lds_u32(lr + 4u * lr_slot(r[t]));
                     }
-                    changed = best >= 0 || tick == 0u;
-                    if (best < 0 && tick != 0u && failed != 3u) { failed = 3u; last_change = tick - 1u; }
+                    uint32_t cl[4], ch[4];
+                    cl[0] = prmt(o[0], o[1], 0x5410); ch[0] = prmt(o[2], o[3], 0x5410);   // stored rows, toward low
+                    cl[1] = prmt(o[0], o[1], 0x7632); ch[1] = prmt(o[2], o[3], 0x7632);   // stored rows, toward high
+                    cl[2] = prmt(o[4], o[5], 0x5410); ch[2] = prmt(o[6], o[7], 0x5410);   // other axis, toward low
+                    cl[3] = prmt(o[4], o[5], 0x7632); ch[3] = prmt(o[6], o[7], 0x7632);
+                    // action labels: stored rows are UP/DOWN (0,1) when stored transposed, else LEFT/RIGHT (2,3)
+                    const uint32_t lab0 = stored_t ? 0u : 2u, lab2 = 2u - lab0;
+                    const uint32_t rr = aw >> 30;
+                    int best = -1;
+                    uint32_t bl = lo, bh = hi, bflip = 0u;
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; c++) {
+                        const uint32_t sl = c < 2 ? lo : yl, sh = c < 2 ? hi : yh;
+                        const uint32_t label = (c < 2 ? lab0 : lab2) + (c & 1u);
+                        const bool valid = ((cl[c] ^ sl) | (ch[c] ^ sh)) != 0u;
+                        const int key = valid ? (int)(blank_count(cl[c], ch[c]) * 4u + (3u - ((label - rr) & 3u))) : -1;
+                        if (key > best) { best = key; bl = cl[c]; bh = ch[c]; taken = label; bflip = c < 2 ? 0u : 1u; }
+                    }
+                    changed = best >= 0 || (j == 0 && tick == 0u);
+                    if (best < 0 && !(j == 0 && tick == 0u) && failed != 3u) { failed = 3u; last_change = tick - 1u; }
                     lo = bl; hi = bh;
+                    if (bflip) axis_word ^= 0x80000000u;
                 }
                 if (RECORD) {
-                    // Ticks enter the loop in pairs starting at an even tick, so slot s = tick - 1 is
-                    // odd in the first half and even in the second: j = s & 3 is {1,3} / {0,2}.
+                    // Ticks enter the loop four at a time starting at a multiple of 4, so the slot
+                    // s = tick - 1 of position j sits at (j + 3) & 3 of its 4-slot group.
                     const uint32_t s = tick - 1u;
                     const bool rec = s < rec_len;                // steps 1..length of a live episode
-                    const bool upper = (s & 2u) != 0u;
-                    const int jl = 1 - half, ju = 3 - half;      // static after unrolling
-                    if (rec && !upper) { tb_lo[jl] = olo; tb_hi[jl] = ohi; }
-                    if (rec && upper) { tb_lo[ju] = olo; tb_hi[ju] = ohi; }
-                    if (rec) tact = __byte_perm(tact, taken, upper ? (ju == 3 ? 0x4210 : 0x3410) : (jl == 1 ? 0x3240 : 0x3214));
-                    const bool flush = rec && ((s & 3u) == 3u || s + 1u == rec_len);
+                    constexpr int kShift[4] = {3, 0, 1, 2};
+                    const int g = kShift[j];                     // static after unrolling
+                    if (rec) {
+                        tb_lo[g] = rec_b_lo; tb_hi[g] = rec_b_hi;
+                        tact = __byte_perm(tact, taken, g == 0 ? 0x3214 : g == 1 ? 0x3240 : g == 2 ? 0x3410 : 0x4210);
+                    }
+                    const bool flush = rec && (g == 3 || s + 1u == rec_len);
                     if (flush) {
-                        const uint64_t g = rec_off + (s & ~3u);
-                        uint4 *dst = (uint4 *)(p.traj_boards + g);
+                        const uint64_t gpos = rec_off + (s & ~3u);
+                        uint4 *dst = (uint4 *)(p.traj_boards + gpos);
                         dst[0] = make_uint4(tb_lo[0], tb_hi[0], tb_lo[1], tb_hi[1]);
                         dst[1] = make_uint4(tb_lo[2], tb_hi[2], tb_lo[3], tb_hi[3]);
-                        *(uint32_t *)(p.traj_actions + g) = tact;
+                        *(uint32_t *)(p.traj_actions + gpos) = tact;
                     }
                 }
                 const Blanks b = count_blanks(lo, hi);
-                const uint32_t v29 = changed ? (vw < R48_SPAWN4_THRESHOLD ? (2u << 29) : (1u << 29)) : 0u;
-                place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), v29);
+                place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), spawn_v29(aw, changed));
                 if (POLICY == kPolicyRandom) {
                     // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
                     const uint32_t axis = 2u - (aw >> 31);
@@ -610,8 +782,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
             }
         };
         // parked lanes (live == false) sit on the empty board
-        if (__all_sync(kFull, tick < 4000u || !live)) two_ticks(std::false_type{});
-        else two_ticks(std::true_type{});
+        if (__all_sync(kFull, tick < 4000u || !live)) four_ticks(std::false_type{});
+        else four_ticks(std::true_type{});
     }
 }
 
@@ -716,6 +888,197 @@ __global__ void __launch_bounds__(256) encode_kernel(const int32_t *__restrict__
     if (bad && status) atomicOr(status, 2);
 }
 
+// ------------------------------------------------------------------ compact episode records
+// One uint32 per episode for the host: score / 2 in bits 31..13 (the sum of a board's tiles is even
+// and at most 16 * 32768 = 2^19, so 19 bits hold it exactly), min(length, 8191) in bits 12..0.
+__global__ void __launch_bounds__(256) records_kernel(const uint64_t *__restrict__ boards,
+                                                      const uint32_t *__restrict__ lengths,
+                                                      uint32_t *records, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = boards[i];
+        const uint32_t sc = board_score((uint32_t)b, (uint32_t)(b >> 32));
+        records[i] = ((sc >> 1) << 13) | min(lengths[i], 8191u);
+    }
+}
+
+// ------------------------------------------------------------------ transition ring
+// Replay.store / Replay.sample (algorithm/ddpg/replay.py:8-47) for batches of transitions, as five
+// device arrays of `capacity` slots: state, action, reward, next_state, done.
+
+struct RingAppendParams {
+    RingRefs ring;
+    const uint64_t *state;
+    const uint8_t *action;
+    const int32_t *reward;       // may be NULL (stored as 0, the reference's reward)
+    const uint64_t *next_state;
+    const uint8_t *done;         // may be NULL (stored as 0)
+    uint64_t n;
+    int drop_when_full;          // Replay.store: a full buffer ignores the transition (replay.py:18-21)
+};
+
+__global__ void __launch_bounds__(256) ring_append_kernel(RingAppendParams p)
+{
+    const uint64_t cap = p.ring.capacity, cur = p.ring.cursor[0];
+    uint64_t skip = 0, at = 0, take = p.n;
+    if (p.drop_when_full) {
+        const uint64_t room = cur < cap ? cap - cur : 0ull;
+        take = p.n < room ? p.n : room;                // the first `take` transitions fit
+        at = cur;
+    } else {
+        at = ring_start(p.ring, p.n, skip);
+    }
+    for (uint64_t i = skip + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < take;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t slot = at + (i - skip);
+        if (slot >= cap) slot -= cap;
+        p.ring.state[slot] = p.state[i];
+        p.ring.action[slot] = p.action[i];
+        p.ring.reward[slot] = p.reward ? p.reward[i] : 0;
+        p.ring.next_state[slot] = p.next_state[i];
+        p.ring.done[slot] = p.done ? p.done[i] : (uint8_t)0;
+    }
+    ring_finish(p.ring, take);
+}
+
+// A keyed pseudo-random permutation of [0, size): six Feistel rounds on 2h >= log2(size) bits,
+// cycle-walked back into range.  perm(0), perm(1), ... are distinct by construction, so the
+// first B values are a sample WITHOUT replacement (random.sample, replay.py:33).
+struct RingPerm {
+    uint32_t k0[6], k1[6];
+    uint32_t half_bits;
+    uint64_t size;
+};
+
+__device__ __forceinline__ uint64_t ring_perm(const RingPerm &P, uint64_t x)
+{
+    const uint32_t h = P.half_bits;
+    const uint32_t mask = h >= 32u ? 0xFFFFFFFFu : ((1u << h) - 1u);
+    do {
+        uint32_t L = (uint32_t)(x >> h) & mask, R = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const uint64_t m = (uint64_t)(R + P.k0[r]) * R48_PHILOX_M0;
+            const uint32_t f = ((uint32_t)(m >> 32) ^ (uint32_t)m ^ P.k1[r]) & mask;
+            const uint32_t t = L ^ f;
+            L = R; R = t;
+        }
+        x = ((uint64_t)L << h) | R;
+    } while (x >= P.size);
+    return x;
+}
+
+struct RingSampleParams {
+    RingRefs ring;
+    uint64_t batch;
+    uint64_t seed, draw;
+    int with_replacement;
+    PhiloxKeys keys;
+    int64_t *out_index;          // may be NULL
+    uint64_t *out_state;
+    uint8_t *out_action;
+    int32_t *out_reward;
+    uint64_t *out_next;
+    uint8_t *out_done;
+    float *obs_state;            // may be NULL: float32 [batch][4][4]
+    float *obs_next;             // may be NULL
+    int obs_log2;
+};
+
+// round keys of the permutation: words 0,1 of Philox(ctr = (draw.lo, draw.hi, r, 'RING'), key = seed)
+__device__ inline void ring_perm_keys(RingPerm &P, uint64_t size, uint64_t draw, const uint32_t (&k0)[kPhiloxRounds],
+                                               const uint32_t (&k1)[kPhiloxRounds])
+{
+    uint32_t bits = 2;
+    while (bits < 64u && ((uint64_t)1 << bits) < size) bits++;
+    P.half_bits = (bits + 1u) / 2u;
+    P.size = size;
+    for (int r = 0; r < 6; r++) {
+        uint32_t c0 = (uint32_t)draw, c1 = (uint32_t)(draw >> 32), c2 = (uint32_t)r, c3 = 0x52494E47u;
+        for (int q = 0; q < kPhiloxRounds; q++) {
+            const uint64_t p0 = (uint64_t)R48_PHILOX_M0 * c0, p1 = (uint64_t)R48_PHILOX_M1 * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0[q], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1[q];
+            c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        }
+        P.k0[r] = c0; P.k1[r] = c1;
+    }
+}
+
+__device__ __forceinline__ void decode_row4(uint32_t w, int log2_planes, float (&v)[4])
+{
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const uint32_t e = (w >> (4 * t)) & 15u;
+        v[t] = log2_planes ? (float)e : (float)((1u << e) & ~1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) ring_sample_kernel(RingSampleParams p)
+{
+    __shared__ RingPerm sperm;
+    const uint64_t cap = p.ring.capacity, cur = p.ring.cursor[0];
+    const uint64_t size = cur < cap ? cur : cap;
+    if (threadIdx.x == 0) {
+        ring_perm_keys(sperm, size > 0 ? size : 1, p.draw, p.keys.k0, p.keys.k1);
+    }
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.batch;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t idx = -1;
+        if (size > 0) {
+            if (p.with_replacement) {
+                // element i of draw `draw`: words 0,1 of Philox(ctr = (i.lo, i.hi, draw.lo, 'SMPL' ^ draw.hi))
+                uint32_t w[4];
+                philox4x32((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)p.draw, 0x534D504Cu ^ (uint32_t)(p.draw >> 32), p.keys, w);
+                idx = (int64_t)__umul64hi(((uint64_t)w[0] << 32) | w[1], size);
+            } else if (i < size) {
+                idx = (int64_t)ring_perm(sperm, i);      // i >= size: the reference returns the whole list
+            }
+        }
+        if (p.out_index) p.out_index[i] = idx;
+        if (idx < 0) continue;
+        const uint64_t s = p.ring.state[idx], nx = p.ring.next_state[idx];
+        p.out_state[i] = s;
+        p.out_next[i] = nx;
+        p.out_action[i] = p.ring.action[idx];
+        p.out_reward[i] = p.ring.reward[idx];
+        p.out_done[i] = p.ring.done[idx];
+        if (p.obs_state || p.obs_next) {
+#pragma unroll
+            for (int row = 0; row < 4; row++) {
+                float v[4];
+                if (p.obs_state) {
+                    decode_row4((uint32_t)(s >> (16 * row)) & 0xFFFFu, p.obs_log2, v);
+                    ((float4 *)p.obs_state)[4ull * i + row] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                if (p.obs_next) {
+                    decode_row4((uint32_t)(nx >> (16 * row)) & 0xFFFFu, p.obs_log2, v);
+                    ((float4 *)p.obs_next)[4ull * i + row] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void ring_clear_kernel(uint64_t *cursor) { cursor[0] = 0ull; cursor[1] = 0ull; }
+
+// 22 B per board in, 22 B out, nothing else: the same memory traffic as step_kernel with no work
+// in between -- what "100 % of HBM" means for a launch of this shape and size (bench.py).
+__global__ void __launch_bounds__(kThreads, 1) copy22_kernel(const uint64_t *__restrict__ in,
+                                                             const uint8_t *__restrict__ action,
+                                                             uint64_t *out, int32_t *reward, uint8_t *done, uint32_t n)
+{
+    const uint32_t pairs = n >> 1;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < pairs; j += gridDim.x * blockDim.x) {
+        const ulonglong2 b = ((const ulonglong2 *)in)[j];
+        const uchar2 a = ((const uchar2 *)action)[j];
+        ((ulonglong2 *)out)[j] = b;
+        ((int2 *)reward)[j] = make_int2(a.x, a.y);
+        ((uchar2 *)done)[j] = a;
+    }
+}
+
 }  // namespace r48
 
 using namespace r48;
@@ -752,8 +1115,8 @@ struct DeviceState {
     uint16_t *left = nullptr;
     uint8_t *merges = nullptr;
     uint32_t *lr = nullptr;
-    Tables tables() const { return Tables{left, merges, lr}; }
-    // host-API arena
+    Tables tables() const { return Tables{left, merges, lr, PipeConsts{1u << 16, 1u << 18}}; }
+    // host-API arena (guarded by g_host_mu[device])
     uint8_t *arena = nullptr;
     size_t arena_bytes = 0;
     cudaStream_t stream = nullptr;
@@ -762,12 +1125,55 @@ struct DeviceState {
 };
 
 DeviceState g_dev[kMaxDevices];
-std::mutex g_mu;
+std::mutex g_mu;                         // guards g_dev[].ready / table construction
+std::mutex g_host_mu[kMaxDevices];       // one *_host call at a time per device (arena, streams, events)
+
+// switches the current device for a scope and always switches back, error paths included
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 template <typename K>
 cudaError_t opt_in_smem(K kernel, uint32_t bytes)
 {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int init_device_locked(int dev, DeviceState &d)
+{
+    DeviceGuard g(dev);
+    CK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaMalloc(&d.left, kLeftBytes));
+    CK(cudaMalloc(&d.merges, kMergeBytes));
+    CK(cudaMalloc(&d.lr, kLrBytes));
+    build_tables_kernel<<<256, 256>>>(d.left, d.merges, d.lr);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(opt_in_smem(step_kernel<false, false, true>, kLrBytes));
+    CK(opt_in_smem(step_kernel<false, false, false>, kLrBytes));
+    CK(opt_in_smem(step_kernel<false, true, true>, kLrBytes));
+    CK(opt_in_smem(step_kernel<false, true, false>, kLrBytes));
+    CK(opt_in_smem(step_kernel<true, false, true>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(step_kernel<true, false, false>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(step_kernel<true, true, true>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(step_kernel<true, true, false>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(env_step_kernel<false>, kLrBytes));
+    CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
+    CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
+    CK(opt_in_smem(rollout_kernel<kPolicyRandom, false>, kLrBytes));
+    CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, false>, kLrBytes));
+    CK(opt_in_smem(rollout_kernel<kPolicyRandom, true>, kLrBytes));
+    CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, true>, kLrBytes));
+    return R48_OK;
 }
 
 int ensure_device(int dev, DeviceState **out)
@@ -776,33 +1182,8 @@ int ensure_device(int dev, DeviceState **out)
     std::lock_guard<std::mutex> lock(g_mu);
     DeviceState &d = g_dev[dev];
     if (!d.ready) {
-        int prev = 0;
-        CK(cudaGetDevice(&prev));
-        CK(cudaSetDevice(dev));
-        CK(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaMalloc(&d.left, kLeftBytes));
-        CK(cudaMalloc(&d.merges, kMergeBytes));
-        CK(cudaMalloc(&d.lr, kLrBytes));
-        build_tables_kernel<<<256, 256>>>(d.left, d.merges, d.lr);
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
-        CK(opt_in_smem(step_kernel<false, false, true>, kLrBytes));
-        CK(opt_in_smem(step_kernel<false, false, false>, kLrBytes));
-        CK(opt_in_smem(step_kernel<false, true, true>, kLrBytes));
-        CK(opt_in_smem(step_kernel<false, true, false>, kLrBytes));
-        CK(opt_in_smem(step_kernel<true, false, true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(step_kernel<true, false, false>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(step_kernel<true, true, true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(step_kernel<true, true, false>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(env_step_kernel<false>, kLrBytes));
-        CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
-        CK(opt_in_smem(afterstates_kernel<true>, kLeftBytes + kMergeBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyRandom, false>, kLrBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, false>, kLrBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyRandom, true>, kLrBytes));
-        CK(opt_in_smem(rollout_kernel<kPolicyGreedyBlanks, true>, kLrBytes));
-        CK(cudaSetDevice(prev));
+        const int rc = init_device_locked(dev, d);      // the guard inside restores the caller's device
+        if (rc) return rc;
         d.ready = true;
     }
     *out = &d;
@@ -820,13 +1201,27 @@ PhiloxKeys make_keys(uint64_t seed)
 {
     PhiloxKeys k;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < kPhiloxRounds; r++) {
         k.k0[r] = k0;
         k.k1[r] = k1;
         k0 += R48_PHILOX_W0;
         k1 += R48_PHILOX_W1;
     }
     return k;
+}
+
+// the launch-constant half of Philox rounds 0..2 for (id.hi, tick): see philox_launch_word
+PhiloxLaunch make_philox_launch(const PhiloxKeys &k, uint32_t id_hi, uint32_t tick)
+{
+    PhiloxLaunch p;
+    const uint64_t p1 = (uint64_t)R48_PHILOX_M1 * (tick >> 2);
+    p.r0_n0 = (uint32_t)(p1 >> 32) ^ id_hi ^ k.k0[0];
+    p.r1_c1k = (uint32_t)p1 ^ k.k0[1];
+    const uint64_t q0 = (uint64_t)R48_PHILOX_M0 * p.r0_n0;
+    p.r1_h0k = (uint32_t)(q0 >> 32) ^ k.k1[1];
+    p.r2_c3k = (uint32_t)q0 ^ k.k1[2];
+    p.word = tick & 3u;
+    return p;
 }
 
 inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
@@ -869,21 +1264,35 @@ cudaError_t launch_pdl(void (*kernel)(P), int grid, int block, uint32_t smem, cu
     return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
+// `whole` describes the full batch (n in whole_n, first id in board_base); launches are cut at
+// 2^30 boards and wherever the global id crosses a multiple of 2^32, so that id.hi is a constant
+// of every launch (PhiloxLaunch).
 template <bool INJECT>
-int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, cudaStream_t s)
+int launch_step(StepParams whole, int64_t whole_n, uint64_t seed, uint64_t board_base, uint32_t tick,
+                int reward_mode, const DeviceState &d, cudaStream_t s)
 {
-    for (int64_t off = 0; off < whole.n; off += kChunk) {
+    const PhiloxKeys keys = make_keys(seed);
+    for (int64_t off = 0; off < whole_n;) {
+        const uint64_t id0 = board_base + (uint64_t)off;
+        int64_t m = whole_n - off < kChunk ? whole_n - off : kChunk;
+        const uint64_t to_wrap = ((uint64_t)1 << 32) - (id0 & 0xFFFFFFFFull);
+        if (!INJECT && (uint64_t)m > to_wrap) m = (int64_t)to_wrap;
         StepParams p = whole;
-        p.n = whole.n - off < kChunk ? whole.n - off : kChunk;
-        p.in += off; p.action += off; p.out += off; p.board_base += (uint64_t)off;
+        p.n = (uint32_t)m;
+        p.in += off; p.action += off; p.out += off;
         if (p.reward) p.reward += off;
         if (p.done) p.done += off;
         if (INJECT) { p.spawn_k += off; p.spawn_exp += off; }
+        p.id_lo = (uint32_t)id0;
+        p.keys = keys;
+        p.pl = make_philox_launch(keys, (uint32_t)(id0 >> 32), tick);
         const bool vec = aligned(p.in, 16) && aligned(p.out, 16) && aligned(p.action, 2) &&
                          (!p.reward || aligned(p.reward, 8)) && (!p.done || aligned(p.done, 2)) &&
                          (!INJECT || (aligned(p.spawn_k, 2) && aligned(p.spawn_exp, 2)));
-        const int64_t units = vec ? (p.n + 1) / 2 : p.n;
-        const int grid = grid_for(units, kThreads, d.sms, 1);
+        // one CTA per SM as soon as there is a warp's worth of units for each (a CTA costs the same
+        // table staging whether it has work for 1 warp or for 32)
+        const int64_t units = vec ? (m + 1) / 2 : m;
+        const int grid = grid_for(units, 32, d.sms, 1);
         const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
         if (reward_mode) {
             if (vec) CK(launch_pdl(step_kernel<true, INJECT, true>, grid, kThreads, smem, s, p));
@@ -892,10 +1301,12 @@ int launch_step(const StepParams &whole, int reward_mode, const DeviceState &d, 
             if (vec) CK(launch_pdl(step_kernel<false, INJECT, true>, grid, kThreads, smem, s, p));
             else CK(launch_pdl(step_kernel<false, INJECT, false>, grid, kThreads, smem, s, p));
         }
+        off += m;
     }
     return R48_OK;
 }
 
+// the arena only grows; callers hold g_host_mu[device]
 int arena_reserve(DeviceState &d, size_t bytes)
 {
     if (!d.stream) CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
@@ -916,11 +1327,16 @@ int arena_reserve(DeviceState &d, size_t bytes)
 
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
+int ring_refs(const r48_ring *ring, RingRefs *out, const char *who)
+{
+    if (!ring || !ring->state || !ring->action || !ring->reward || !ring->next_state || !ring->done || !ring->cursor)
+        return fail(R48_ERR_NULL, who);
+    if (ring->capacity == 0 || ring->capacity > ((uint64_t)1 << 40)) return fail(R48_ERR_ARG, "ring capacity must be in 1 .. 2^40");
+    if (!aligned(ring->state, 8) || !aligned(ring->next_state, 8) || !aligned(ring->reward, 4) || !aligned(ring->cursor, 8))
+        return fail(R48_ERR_ALIGN, "ring arrays are misaligned");
+    *out = RingRefs{ring->state, ring->action, ring->reward, ring->next_state, ring->done, ring->cursor, ring->capacity};
+    return R48_OK;
+}
 
 }  // namespace
 
@@ -929,6 +1345,11 @@ struct DeviceGuard {
 extern "C" {
 
 int r48_version(void) { return R48_VERSION; }
+
+#ifndef R48_BUILD_ID
+#define R48_BUILD_ID "unknown"
+#endif
+const char *r48_build_id(void) { return "R48_BUILD_ID=" R48_BUILD_ID; }
 
 const char *r48_last_error(void) { return g_err; }
 
@@ -979,9 +1400,10 @@ int r48_step(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *
         return fail(R48_ERR_ALIGN, "r48_step: misaligned pointer");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
-    StepParams p{in, action, nullptr, nullptr, out, reward, done, status, n, board_base,
-                 step + 1u, make_keys(seed), d->tables()};
-    return launch_step<false>(p, reward_mode, *d, (cudaStream_t)stream);
+    StepParams p{};
+    p.in = in; p.action = action; p.out = out; p.reward = reward; p.done = done; p.status = status;
+    p.tables = d->tables();
+    return launch_step<false>(p, n, seed, board_base, step + 1u, reward_mode, *d, (cudaStream_t)stream);
 }
 
 int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *spawn_k,
@@ -999,15 +1421,17 @@ int r48_step_injected(const uint64_t *in, const uint8_t *action, const uint8_t *
         return fail(R48_ERR_ALIGN, "r48_step_injected: misaligned pointer");
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
-    StepParams p{in, action, spawn_k, spawn_exp, out, reward, done, status, n, 0ull,
-                 0u, make_keys(0), d->tables()};
-    return launch_step<true>(p, reward_mode, *d, (cudaStream_t)stream);
+    StepParams p{};
+    p.in = in; p.action = action; p.spawn_k = spawn_k; p.spawn_exp = spawn_exp;
+    p.out = out; p.reward = reward; p.done = done; p.status = status;
+    p.tables = d->tables();
+    return launch_step<true>(p, n, 0ull, 0ull, 0u, reward_mode, *d, (cudaStream_t)stream);
 }
 
-int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
-                 int32_t *reward, uint8_t *done, float *obs, int obs_mode, uint64_t *final_boards,
-                 int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
-                 int reward_mode, int auto_reset, int32_t *status, void *stream)
+int r48_env_step_ring(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
+                      int32_t *reward, uint8_t *done, float *obs, int obs_mode, uint64_t *final_boards,
+                      int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
+                      int reward_mode, int auto_reset, int32_t *status, const r48_ring *ring, void *stream)
 {
     int rc = check_n(n);
     if (rc) return rc;
@@ -1019,6 +1443,11 @@ int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint3
     if (!aligned(boards, 8) || !aligned(steps, 4) || !aligned(episodes, 4) || (reward && !aligned(reward, 4)) ||
         (obs && !aligned(obs, 16)) || (final_boards && !aligned(final_boards, 8)) || (status && !aligned(status, 4)))
         return fail(R48_ERR_ALIGN, "r48_env_step: misaligned pointer");
+    RingRefs rr{};
+    if (ring) {
+        if ((rc = ring_refs(ring, &rr, "r48_env_step_ring: NULL ring array"))) return rc;
+        if (n > kChunk) return fail(R48_ERR_ARG, "r48_env_step_ring: at most 2^30 envs per call with a ring");
+    }
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     for (int64_t off = 0; off < n; off += kChunk) {
@@ -1026,7 +1455,7 @@ int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint3
         EnvParams p{boards + off, action + off, steps + off, episodes + off, reward ? reward + off : nullptr,
                     done ? done + off : nullptr, obs ? obs + 16 * off : nullptr,
                     final_boards ? final_boards + off : nullptr, status, (uint32_t)m,
-                    board_base + (uint64_t)off, id_stride, obs_mode, auto_reset, make_keys(seed), d->tables()};
+                    board_base + (uint64_t)off, id_stride, obs_mode, auto_reset, make_keys(seed), d->tables(), rr};
         const int grid = grid_for(m, kThreads, d->sms, 1);
         if (reward_mode)
             CK(launch_pdl(env_step_kernel<true>, grid, kThreads, kLeftBytes + kMergeBytes, (cudaStream_t)stream, p));
@@ -1034,6 +1463,15 @@ int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint3
             CK(launch_pdl(env_step_kernel<false>, grid, kThreads, kLrBytes, (cudaStream_t)stream, p));
     }
     return R48_OK;
+}
+
+int r48_env_step(uint64_t *boards, const uint8_t *action, uint32_t *steps, uint32_t *episodes,
+                 int32_t *reward, uint8_t *done, float *obs, int obs_mode, uint64_t *final_boards,
+                 int64_t n, uint64_t seed, uint64_t board_base, uint64_t id_stride,
+                 int reward_mode, int auto_reset, int32_t *status, void *stream)
+{
+    return r48_env_step_ring(boards, action, steps, episodes, reward, done, obs, obs_mode, final_boards, n, seed,
+                             board_base, id_stride, reward_mode, auto_reset, status, nullptr, stream);
 }
 
 int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,
@@ -1123,6 +1561,22 @@ int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int
     return R48_OK;
 }
 
+int r48_episode_records(const uint64_t *final_boards, const uint32_t *lengths, uint32_t *records,
+                        int64_t n, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!final_boards || !lengths || !records) return fail(R48_ERR_NULL, "r48_episode_records: NULL pointer");
+    if (!aligned(final_boards, 8) || !aligned(lengths, 4) || !aligned(records, 4))
+        return fail(R48_ERR_ALIGN, "r48_episode_records: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    records_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(final_boards, lengths, records, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
 int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy,
                        uint64_t *final_boards, uint32_t *lengths, uint64_t *stats, void *workspace,
                        void *stream)
@@ -1139,7 +1593,7 @@ int r48_rollout_policy(int64_t n, uint64_t seed, uint64_t board_base, int policy
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    constexpr int64_t kRolloutChunk = (int64_t)1 << 31;      // the kernel's episode queue is 32-bit
+    constexpr int64_t kRolloutChunk = (int64_t)1 << 30;      // the kernel's episode queue is 32-bit
     for (int64_t off = 0; off < n; off += kRolloutChunk) {
         const int64_t m = n - off < kRolloutChunk ? n - off : kRolloutChunk;
         CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
@@ -1172,7 +1626,7 @@ int r48_rollout_trajectories(int64_t n, uint64_t seed, uint64_t board_base, int 
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    constexpr int64_t kRolloutChunk = (int64_t)1 << 31;
+    constexpr int64_t kRolloutChunk = (int64_t)1 << 30;
     for (int64_t off = 0; off < n; off += kRolloutChunk) {
         const int64_t m = n - off < kRolloutChunk ? n - off : kRolloutChunk;
         CK(cudaMemsetAsync(workspace, 0, R48_ROLLOUT_WORKSPACE_BYTES, s));
@@ -1257,7 +1711,82 @@ int r48_encode_i32(const int32_t *values, uint64_t *boards, int64_t n, int32_t *
     return R48_OK;
 }
 
+// ---------------------------------------------------------------- transition ring
+
+int r48_ring_clear(const r48_ring *ring, void *stream)
+{
+    if (!ring || !ring->cursor) return fail(R48_ERR_NULL, "r48_ring_clear: NULL ring");
+    if (!aligned(ring->cursor, 8)) return fail(R48_ERR_ALIGN, "r48_ring_clear: cursor not 8-byte aligned");
+    ring_clear_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ring->cursor);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_ring_append(const r48_ring *ring, const uint64_t *state, const uint8_t *action,
+                    const int32_t *reward, const uint64_t *next_state, const uint8_t *done, int64_t n,
+                    int drop_when_full, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    RingRefs rr;
+    if ((rc = ring_refs(ring, &rr, "r48_ring_append: NULL ring array"))) return rc;
+    if (n == 0) return R48_OK;
+    if (!state || !action || !next_state) return fail(R48_ERR_NULL, "r48_ring_append: state/action/next_state is NULL");
+    if (!aligned(state, 8) || !aligned(next_state, 8) || (reward && !aligned(reward, 4)))
+        return fail(R48_ERR_ALIGN, "r48_ring_append: misaligned pointer");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    RingAppendParams p{rr, state, action, reward, next_state, done, (uint64_t)n, drop_when_full != 0};
+    ring_append_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_ring_sample(const r48_ring *ring, int64_t batch, uint64_t seed, uint64_t draw, int with_replacement,
+                    int64_t *out_index, uint64_t *out_state, uint8_t *out_action, int32_t *out_reward,
+                    uint64_t *out_next_state, uint8_t *out_done, float *obs_state, float *obs_next_state,
+                    int obs_mode, void *stream)
+{
+    int rc = check_n(batch);
+    if (rc) return rc;
+    RingRefs rr;
+    if ((rc = ring_refs(ring, &rr, "r48_ring_sample: NULL ring array"))) return rc;
+    if (obs_mode != 0 && obs_mode != 1) return fail(R48_ERR_ARG, "r48_ring_sample: obs_mode must be 0 or 1");
+    if (batch == 0) return R48_OK;
+    if (!out_state || !out_action || !out_reward || !out_next_state || !out_done)
+        return fail(R48_ERR_NULL, "r48_ring_sample: NULL output");
+    if (!aligned(out_state, 8) || !aligned(out_next_state, 8) || !aligned(out_reward, 4) ||
+        (out_index && !aligned(out_index, 8)) || (obs_state && !aligned(obs_state, 16)) ||
+        (obs_next_state && !aligned(obs_next_state, 16)))
+        return fail(R48_ERR_ALIGN, "r48_ring_sample: misaligned output");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    RingSampleParams p{rr, (uint64_t)batch, seed, draw, with_replacement != 0, make_keys(seed), out_index, out_state,
+                       out_action, out_reward, out_next_state, out_done, obs_state, obs_next_state, obs_mode};
+    ring_sample_kernel<<<grid_for(batch, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_debug_copy22(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward, uint8_t *done,
+                     int64_t n, void *stream)
+{
+    if (n <= 0 || n > kChunk || (n & 1)) return fail(R48_ERR_ARG, "r48_debug_copy22: n must be even, 2 .. 2^30");
+    if (!in || !action || !out || !reward || !done) return fail(R48_ERR_NULL, "r48_debug_copy22: NULL pointer");
+    if (!aligned(in, 16) || !aligned(out, 16) || !aligned(reward, 8) || !aligned(action, 2) || !aligned(done, 2))
+        return fail(R48_ERR_ALIGN, "r48_debug_copy22: misaligned pointer");
+    DeviceState *d;
+    int rc;
+    if ((rc = current_device(&d))) return rc;
+    copy22_kernel<<<grid_for(n / 2, kThreads, d->sms, 2), kThreads, 0, (cudaStream_t)stream>>>(in, action, out, reward, done, (uint32_t)n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
+// Each call holds its device's host mutex from the first arena access to the last
+// synchronise: calls from several threads on one device serialise, calls on different devices
+// run concurrently.
 
 int r48_step_host(const uint64_t *in, const uint8_t *action, uint64_t *out, int32_t *reward,
                   uint8_t *done, int64_t n, uint64_t seed, uint64_t board_base, uint32_t step,
@@ -1269,6 +1798,7 @@ int r48_step_host(const uint64_t *in, const uint8_t *action, uint64_t *out, int3
     if (!in || !action || !out) return fail(R48_ERR_NULL, "r48_step_host: in/action/out is NULL");
     DeviceState *d;
     if ((rc = ensure_device(device, &d))) return rc;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[device]);
     DeviceGuard g(device);
     const size_t nb = (size_t)n;
     const size_t o_board = 0, o_act = up256(nb * 8), o_rew = o_act + up256(nb),
@@ -1316,6 +1846,7 @@ int r48_afterstates_host(const uint64_t *in, uint64_t *out, int32_t *reward, uin
     if (!in || !out) return fail(R48_ERR_NULL, "r48_afterstates_host: in/out is NULL");
     DeviceState *d;
     if ((rc = ensure_device(device, &d))) return rc;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[device]);
     DeviceGuard g(device);
     const size_t nb = (size_t)n;
     const size_t o_in = 0, o_out = up256(nb * 8), o_rew = o_out + up256(nb * 32),
@@ -1337,21 +1868,26 @@ int r48_afterstates_host(const uint64_t *in, uint64_t *out, int32_t *reward, uin
     return R48_OK;
 }
 
-int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
-                     uint32_t *lengths, uint64_t *stats, int device)
+int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int policy, uint64_t *final_boards,
+                        uint32_t *lengths, uint32_t *records, uint64_t *stats, int device)
 {
     int rc = check_n(n);
     if (rc) return rc;
+    if (policy != R48_POLICY_RANDOM && policy != R48_POLICY_GREEDY_BLANKS)
+        return fail(R48_ERR_ARG, "r48_rollout_host_ex: unknown policy");
     if (n == 0) return R48_OK;
     DeviceState *d;
     if ((rc = ensure_device(device, &d))) return rc;
+    std::lock_guard<std::mutex> host_lock(g_host_mu[device]);
     DeviceGuard g(device);
     const size_t nb = (size_t)n;
-    const size_t o_fb = 0, o_len = up256(nb * 8), o_stats = o_len + up256(nb * 4),
-                 o_ws = o_stats + up256(R48_STATS_WORDS * 8), total = o_ws + R48_ROLLOUT_WORKSPACE_BYTES;
+    const size_t o_fb = 0, o_len = up256(nb * 8), o_rec = o_len + up256(nb * 4),
+                 o_stats = o_rec + up256(records ? nb * 4 : 0), o_ws = o_stats + up256(R48_STATS_WORDS * 8),
+                 total = o_ws + R48_ROLLOUT_WORKSPACE_BYTES;
     if ((rc = arena_reserve(*d, total))) return rc;
     uint64_t *d_fb = (uint64_t *)(d->arena + o_fb);
     uint32_t *d_len = (uint32_t *)(d->arena + o_len);
+    uint32_t *d_rec = (uint32_t *)(d->arena + o_rec);
     uint64_t *d_stats = (uint64_t *)(d->arena + o_stats);
     cudaStream_t s = d->stream, c = d->copy_stream;
     if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
@@ -1368,16 +1904,19 @@ int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *fi
         else if (left > 2 * big) m = big;
         else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
         else m = left;
-        rc = r48_rollout(m, seed, board_base + (uint64_t)off, d_fb + off, d_len + off,
-                         stats ? d_stats : nullptr, d->arena + o_ws, s);
+        rc = r48_rollout_policy(m, seed, board_base + (uint64_t)off, policy, d_fb + off, d_len + off,
+                                stats ? d_stats : nullptr, d->arena + o_ws, s);
         if (rc) return rc;
-        if (final_boards || lengths) {
+        if (records && (rc = r48_episode_records(d_fb + off, d_len + off, d_rec + off, m, s))) return rc;
+        if (final_boards || lengths || records) {
             CK(cudaEventRecord(d->chunk_done[slot], s));
             CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
             if (final_boards)
                 CK(cudaMemcpyAsync(final_boards + off, d_fb + off, (size_t)m * 8, cudaMemcpyDeviceToHost, c));
             if (lengths)
                 CK(cudaMemcpyAsync(lengths + off, d_len + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+            if (records)
+                CK(cudaMemcpyAsync(records + off, d_rec + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
         }
     }
     if (stats) CK(cudaMemcpyAsync(stats, d_stats, R48_STATS_WORDS * 8, cudaMemcpyDeviceToHost, s));
@@ -1386,10 +1925,17 @@ int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *fi
     return R48_OK;
 }
 
+int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *final_boards,
+                     uint32_t *lengths, uint64_t *stats, int device)
+{
+    return r48_rollout_host_ex(n, seed, board_base, R48_POLICY_RANDOM, final_boards, lengths, nullptr, stats, device);
+}
+
 int r48_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_mu);
     for (int dev = 0; dev < kMaxDevices; dev++) {
+        std::lock_guard<std::mutex> host_lock(g_host_mu[dev]);
         DeviceState &d = g_dev[dev];
         if (!d.ready && !d.arena && !d.stream) continue;
         DeviceGuard g(dev);

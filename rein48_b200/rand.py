@@ -65,7 +65,7 @@ def random_rollouts(n, seed=0, device="cuda", board_base=0, buffers=None, with_s
             buffers.final_boards.data_ptr(),
             buffers.lengths.data_ptr(), buffers.stats.data_ptr() if with_stats else None,
             buffers.workspace.data_ptr(), _stream(dev)))
-    return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats)
+    return RolloutResult(buffers.final_boards[:n], buffers.lengths[:n], buffers.stats if with_stats else None)
 
 
 class Trajectories(namedtuple("Trajectories", "offsets boards actions final_boards lengths stats")):
@@ -121,19 +121,42 @@ def sharded_rollouts(n_total, seed=0, device=None, buffers=None, group=None):
     return res
 
 
-def random_rollouts_host(n, seed=0, device=0, board_base=0, out=None):
-    """End-to-end form over HOST buffers (r48_rollout_host): results land in pinned host
-    tensors.  Returns RolloutResult of CPU tensors."""
+HostRecords = namedtuple("HostRecords", "records stats")
+
+
+def record_scores(records):
+    """score of every episode of a packed record array (main.py:48's np.sum(state_matrix))."""
+    return (records.to(torch.int64) & 0xFFFFFFFF) >> 13 << 1
+
+
+def record_lengths(records):
+    """min(length, 8191) of every episode of a packed record array."""
+    return records.to(torch.int64) & 8191
+
+
+def random_rollouts_host(n, seed=0, device=0, board_base=0, out=None, policy="random", records=False):
+    """End-to-end form over HOST buffers (r48_rollout_host_ex): results land in pinned host
+    tensors.  records=False: RolloutResult(final_boards int64[n], lengths int32[n], stats) --
+    12 bytes per episode cross PCIe; records=True: HostRecords(records int32[n], stats) -- one
+    packed word per episode (score / 2 in bits 31..13, min(length, 8191) below; see
+    record_scores / record_lengths), 4 bytes per episode."""
     if not torch.cuda.is_available():
         raise RuntimeError("rein48_b200 needs a CUDA device (B200, sm_100a); none is visible")
     if out is None:
-        out = RolloutResult(torch.empty(n, dtype=torch.int64).pin_memory(),
-                            torch.empty(n, dtype=torch.int32).pin_memory(),
-                            torch.empty(STATS_WORDS, dtype=torch.int64).pin_memory())
+        stats = torch.empty(STATS_WORDS, dtype=torch.int64).pin_memory()
+        if records:
+            out = HostRecords(torch.empty(n, dtype=torch.int32).pin_memory(), stats)
+        else:
+            out = RolloutResult(torch.empty(n, dtype=torch.int64).pin_memory(),
+                                torch.empty(n, dtype=torch.int32).pin_memory(), stats)
     index = torch.device(device).index if not isinstance(device, int) else device
-    _native.check(_native.lib().r48_rollout_host(
-        int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), out.final_boards.data_ptr(),
-        out.lengths.data_ptr(), out.stats.data_ptr(), int(index or 0)))
+    if records:
+        ptrs = (None, None, out.records.data_ptr())
+    else:
+        ptrs = (out.final_boards.data_ptr(), out.lengths.data_ptr(), None)
+    _native.check(_native.lib().r48_rollout_host_ex(
+        int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, int(board_base), POLICIES[policy], ptrs[0], ptrs[1], ptrs[2],
+        out.stats.data_ptr() if out.stats is not None else None, int(index or 0)))
     return out
 
 
@@ -156,4 +179,4 @@ def play(game, control="rand", show_state=False, show_result=False):
 
 __all__ = ["Rand", "RolloutBuffers", "RolloutResult", "random_rollouts", "sharded_rollouts",
            "rollout_trajectories", "Trajectories",
-           "random_rollouts_host", "play", "EpisodeStats", "scores"]
+           "random_rollouts_host", "HostRecords", "record_scores", "record_lengths", "play", "EpisodeStats", "scores"]

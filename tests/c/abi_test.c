@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #include "r48.h"
 
@@ -16,6 +17,18 @@ int orc_step_batch(const uint64_t *in, const uint8_t *action, uint64_t *out, int
                    int64_t n, uint64_t seed, uint64_t board_base, uint32_t step, int reward_mode);
 void orc_afterstates_batch(const uint64_t *in, uint64_t *out, int32_t *reward, uint8_t *valid, uint8_t *done,
                            int64_t n, int reward_mode);
+
+/* two host threads on one device: the _host entry points serialise on a per-device mutex */
+struct job { int64_t n; uint64_t seed, base; uint64_t *fb; uint32_t *ln; uint32_t *rec; int rc; };
+
+static void *job_main(void *arg)
+{
+    struct job *j = (struct job *)arg;
+    j->rc = 0;
+    for (int rep = 0; rep < 3 && j->rc == 0; rep++)      /* different sizes make the arena grow under the other thread */
+        j->rc = r48_rollout_host_ex(j->n >> (2 - rep), j->seed, j->base, R48_POLICY_RANDOM, j->fb, j->ln, j->rec, NULL, 0);
+    return NULL;
+}
 
 #define CHECK(cond, msg) do { if (!(cond)) { fprintf(stderr, "FAIL: %s (%s)\n", msg, r48_last_error()); return 1; } } while (0)
 
@@ -60,9 +73,30 @@ int main(void)
     CHECK(memcmp(af, oaf, n * 32) == 0 && memcmp(ar, oar, n * 16) == 0 && memcmp(va, ova, n) == 0 &&
           memcmp(dn, odn, n) == 0, "afterstates differ");
 
+    /* r48.h "Threads": concurrent _host calls on one device are safe */
+    struct job jobs[2];
+    pthread_t tid[2];
+    for (int t = 0; t < 2; t++) {
+        jobs[t].n = 40000 + 20000 * t; jobs[t].seed = 7 + t; jobs[t].base = 1000 * t;
+        jobs[t].fb = malloc(jobs[t].n * 8); jobs[t].ln = malloc(jobs[t].n * 4); jobs[t].rec = malloc(jobs[t].n * 4);
+        pthread_create(&tid[t], NULL, job_main, &jobs[t]);
+    }
+    for (int t = 0; t < 2; t++) pthread_join(tid[t], NULL);
+    for (int t = 0; t < 2; t++) {
+        CHECK(jobs[t].rc == R48_OK, "threaded r48_rollout_host_ex");
+        uint64_t *tfb = malloc(jobs[t].n * 8);
+        uint32_t *tln = malloc(jobs[t].n * 4);
+        orc_rollout(jobs[t].n, jobs[t].seed, jobs[t].base, tfb, tln);
+        CHECK(memcmp(jobs[t].fb, tfb, jobs[t].n * 8) == 0 && memcmp(jobs[t].ln, tln, jobs[t].n * 4) == 0,
+              "threaded rollouts differ from the oracle");
+        for (int64_t i = 0; i < jobs[t].n; i += 997)
+            CHECK(R48_RECORD_LENGTH(jobs[t].rec[i]) == (tln[i] < 8191 ? tln[i] : 8191), "record length");
+        free(tfb); free(tln);
+    }
+
     CHECK(r48_rollout_host(-1, 0, 0, fb, ln, st, 0) == R48_ERR_ARG, "negative n accepted");
     CHECK(r48_shutdown() == R48_OK, "shutdown");
-    printf("C ABI ok: %lld episodes, %llu env-steps, step/afterstates bit-exact\n", (long long)n,
+    printf("C ABI ok: %lld episodes, %llu env-steps, step/afterstates bit-exact, 2 host threads ok\n", (long long)n,
            (unsigned long long)st[R48_STATS_SUM_LEN]);
     return 0;
 }

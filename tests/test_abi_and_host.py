@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol(native):
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r"\bT (r48_[a-z0-9_]+)", out)))
     assert exported == declared
-    assert L.r48_version() == 100
+    assert L.r48_version() == 200 == native.VERSION
+    assert native.built_id() == native.source_id() and L.r48_build_id().decode().endswith(native.source_id())
 
 
 def test_header_constants_match_python_and_oracle(native):
@@ -71,6 +72,21 @@ def test_argument_validation_needs_no_device(native):
     assert L.r48_rollout(4, 0, 0, p, None, None, p, None) == native.ERR_NULL
     assert L.r48_rollout(0, 0, 0, None, None, None, None, None) == native.OK
     assert b"NULL" in L.r48_last_error()
+    # transition ring: struct and argument checks
+    ring = native.Ring(p, p, p, p, p, p, 0)
+    assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 1, 0, None) == native.ERR_ARG     # capacity 0
+    ring.capacity = 4
+    ring.reward = None
+    assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 1, 0, None) == native.ERR_NULL
+    ring.reward = p
+    assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 0, 0, None) == native.OK          # empty append
+    assert L.r48_ring_append(ctypes.byref(ring), None, p, None, p, None, 2, 0, None) == native.ERR_NULL
+    assert L.r48_ring_sample(ctypes.byref(ring), 2, 0, 0, 0, None, None, p, p, p, p, None, None, 0, None) == native.ERR_NULL
+    assert L.r48_ring_sample(ctypes.byref(ring), 2, 0, 0, 0, None, p, p, p, p, p, None, None, 7, None) == native.ERR_ARG
+    assert L.r48_ring_clear(None, None) == native.ERR_NULL
+    assert L.r48_rollout_host_ex(-1, 0, 0, 0, None, None, None, None, 0) == native.ERR_ARG
+    assert L.r48_rollout_host_ex(4, 0, 0, 9, None, None, None, None, 0) == native.ERR_ARG             # unknown policy
+    assert L.r48_episode_records(p, p, None, 4, None) == native.ERR_NULL
     with pytest.raises(native.R48Error):
         native.check(L.r48_reset(None, 4, 0, 0, None))
 

@@ -19,7 +19,7 @@ def build_c_test(tmp_path):
     subprocess.check_call([
         "gcc", "-O1", "-std=c11", "-Wall", "-I", os.path.join(ROOT, "include"),
         os.path.join(ROOT, "tests", "c", "abi_test.c"), "-o", exe,
-        "-L", pkg, "-L", orc, "-l:libr48.so", "-l:libr48_oracle.so",
+        "-L", pkg, "-L", orc, "-l:libr48.so", "-l:libr48_oracle.so", "-lpthread",
         "-Wl,-rpath," + pkg, "-Wl,-rpath," + orc])
     return exe
 

@@ -174,14 +174,126 @@ def test_spawn_vs_oracle(r48, orc):
     from rein48_b200.batched import spawn
     spawn(d, SEED, BIG_BASE, tick=5)
     got = to_u64(d)
-    for i in range(0, n, 37):
-        a, v = orc.draw(SEED, BIG_BASE + i, 5)
+    assert (got == orc.spawn_batch(b, SEED, BIG_BASE, 5)).all()
+    for i in range(0, n, 37):                    # and the draw spec spelled out: no move, so row-major
+        a = orc.draw(SEED, BIG_BASE + i, 5)
         m = orc.decode(b[i])
         nb = int((m == 0).sum())
         if nb:
             k = (((a << 2) & 0xFFFFFFFF) * nb) >> 32
-            m, _ = orc.random_fill_grid(m, k, 4 if v < 0x1999999A else 2)
+            m, _ = orc.random_fill_grid(m, k, 4 if (a * orc.VALUE_HASH) & 0xFFFFFFFF < orc.SPAWN4_THRESHOLD else 2)
         assert orc.encode(m) == int(got[i])
+
+
+def test_spawn_injected_out_of_range_k(r48, orc):
+    """any k >= n_blank -- 16, 17 and 255 included -- leaves the board as it is."""
+    b = np.repeat(random_boards(500, 41, p_zero=0.4), 6)
+    blanks = np.array([(orc.decode(x) == 0).sum() for x in b])
+    k = np.tile(np.array([0, 1, 16, 17, 255, 15], np.uint8), 500)
+    k[0::6] = blanks[0::6]                        # exactly n_blank: the first index that is out of range
+    d = boards_to_dev(b)
+    r48.spawn_injected(d, dev(k), dev(np.full(b.size, 2, np.uint8)))
+    got = to_u64(d)
+    for i in range(b.size):
+        m = orc.decode(b[i])
+        if k[i] < blanks[i]:
+            m, _ = orc.random_fill_grid(m, int(k[i]), 4)
+        assert orc.encode(m) == int(got[i]), (i, int(k[i]), int(blanks[i]))
+    # the same through step_injected
+    a = np.random.default_rng(2).integers(0, 4, b.size).astype(np.uint8)
+    env = r48.BatchedGame(b.size)
+    env.boards.copy_(boards_to_dev(b))
+    out, _, _ = env.step_injected(dev(a), dev(k), dev(np.full(b.size, 1, np.uint8)))
+    moved = orc.afterstates_batch(b)[0][a, np.arange(b.size)]
+    for i in range(0, b.size, 7):
+        m = orc.decode(moved[i])
+        nb = int((m == 0).sum())
+        if moved[i] != b[i] and k[i] < nb:
+            m, _ = orc.random_fill_grid(m, int(k[i]), 2)
+        assert orc.encode(m) == int(to_u64(out)[i])
+
+
+def test_step_across_a_2_32_id_boundary(r48, orc):
+    """launches are cut where the global id crosses a multiple of 2^32 (id.hi is a launch constant
+    of the step kernel); the second piece starts at an odd offset and takes the scalar kernel"""
+    n = 5001
+    for base in ((1 << 32) - 1001, (3 << 32) - 2, (1 << 64) - (1 << 32) - 7):
+        b = random_boards(n, 17)
+        a = np.random.default_rng(base % 1000).integers(0, 4, n).astype(np.uint8)
+        env = r48.BatchedGame(n, seed=SEED, board_base=base)
+        assert (to_u64(env.boards) == orc.reset_batch(n, SEED, base)).all()
+        env.boards.copy_(boards_to_dev(b))
+        env.steps = 6
+        boards, _, done = env.step(dev(a))
+        o_b, _, o_d = orc.step_batch(b, a, SEED, base, 6)
+        assert (to_u64(boards) == o_b).all() and (done.cpu().numpy() == o_d).all()
+
+
+def test_reset_starts_a_new_epoch(r48, orc):
+    """reset() must not replay the same games.  Epoch e keys the draws with
+    seed + e * 0x9E3779B97F4A7C15, reproducibly."""
+    n = 4099
+    env = r48.BatchedGame(n, seed=SEED, board_base=5, id_stride=2 * n)
+    first = env.boards.clone()
+    env.env_step(torch.zeros(n, dtype=torch.uint8, device="cuda"))
+    second = env.reset().clone()
+    assert env.epoch == 1 and not bool((first == second).all())
+    assert int(env.env_steps.sum()) == 0 and int(env.env_episodes.sum()) == 0 and env.steps == 0
+    key1 = (SEED + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    assert (to_u64(second) == orc.reset_batch(n, key1, 5)).all()
+    a = np.random.default_rng(1).integers(0, 4, n).astype(np.uint8)
+    boards, _, _ = env.step(dev(a))
+    assert (to_u64(boards) == orc.step_batch(to_u64(second), a, key1, 5, 0)[0]).all()
+    again = r48.BatchedGame(n, seed=SEED, board_base=5)
+    assert (again.reset(epoch=1) == second).all()           # reproducible from (seed, epoch)
+    assert (again.reset(epoch=0) == first).all()
+    shard = r48.BatchedGame(8, seed=1, board_base=64)
+    with pytest.raises(ValueError):                         # a shard must say how big the whole batch is
+        shard.env_step(torch.zeros(8, dtype=torch.uint8, device="cuda"))
+    r48.BatchedGame(8, seed=1, board_base=64, id_stride=128).env_step(torch.zeros(8, dtype=torch.uint8, device="cuda"))
+
+
+def test_dlpack_inputs_are_zero_copy(r48, orc):
+    """north_star: tensors via DLPack, zero-copy.  A capsule / any __dlpack__ producer is accepted
+    wherever a tensor is, without a copy; CPU producers are refused (there is no CPU path)."""
+    from torch.utils.dlpack import to_dlpack
+    from rein48_b200.batched import from_any
+
+    class Foreign:                      # stands in for a cupy / jax array: only speaks the protocol
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None, **kw):
+            return self.t.__dlpack__(stream=stream) if stream is not None else self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    n = 4096
+    b = random_boards(n, 3)
+    d = boards_to_dev(b)
+    a = dev(np.random.default_rng(0).integers(0, 4, n).astype(np.uint8))
+    assert from_any(to_dlpack(d)).data_ptr() == d.data_ptr()
+    assert from_any(Foreign(d)).data_ptr() == d.data_ptr()
+    want = orc.afterstates_batch(b)
+    for src in (to_dlpack(d), Foreign(d)):
+        after, _, valid, done = r48.afterstates(src)
+        assert (to_u64(after) == want[0]).all() and (valid.cpu().numpy() == want[2]).all()
+    assert (r48.decode(Foreign(d)).cpu().numpy() == orc.decode_batch(b)).all()
+    assert (r48.scores(to_dlpack(d))[0].cpu().numpy()[:500] == orc.scores(b[:500])).all()
+    assert (r48.encode(Foreign(r48.decode(d, dtype=torch.int32))) == d).all()
+    env = r48.BatchedGame(n, seed=SEED)
+    env.boards.copy_(d)
+    out, _, _ = env.step(Foreign(a))
+    assert (to_u64(out) == orc.step_batch(b, a.cpu().numpy(), SEED, 0, 0)[0]).all()
+    env.boards.copy_(d)
+    env.steps = 0
+    out, _, _ = env.step(to_dlpack(a))
+    assert (to_u64(out) == orc.step_batch(b, a.cpu().numpy(), SEED, 0, 0)[0]).all()
+    with pytest.raises(RuntimeError):
+        r48.afterstates(Foreign(d.cpu()))
+    with pytest.raises(RuntimeError):
+        r48.afterstates(to_dlpack(d.cpu()))
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -274,7 +386,7 @@ def test_rollout_equals_repeated_step(r48):
     from oracle import oracle as orc
     ids = np.arange(n, dtype=np.uint64) + np.uint64(base)
     while bool(alive.any()):
-        acts = np.array([orc.draw(seed, int(i), env.steps + 1)[0] >> 30 for i in ids], np.uint8)
+        acts = np.array([orc.draw(seed, int(i), env.steps + 1) >> 30 for i in ids], np.uint8)
         boards, _, done = env.step(dev(acts))
         frozen = torch.where(alive, boards, frozen)
         env.boards.copy_(frozen)
@@ -300,6 +412,21 @@ def test_rollout_host_entry(r48, orc):
     assert (out.final_boards.numpy().view(np.uint64) == fb).all()
     assert (out.lengths.numpy().view(np.uint32) == ln).all()
     assert (out.stats.numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
+
+
+def test_rollout_host_records(r48, orc):
+    """the compact per-episode record (one word: score / 2 | length) through the host entry point"""
+    n = 70001
+    out = r48.random_rollouts_host(n, seed=3, board_base=17, records=True)
+    fb, ln = orc.rollout(n, 3, 17, threads=8)
+    rec = out.records.numpy().view(np.uint32)
+    assert (rec == orc.episode_records(fb, ln)).all()
+    assert (r48.record_scores(out.records).numpy() == orc.scores(fb)).all()
+    assert (r48.record_lengths(out.records).numpy() == ln).all()
+    assert (out.stats.numpy().view(np.uint64) == orc.episode_stats(fb, ln)).all()
+    g = r48.random_rollouts_host(3000, seed=3, board_base=17, records=True, policy="greedy_blanks")
+    gfb, gln = orc.rollout_greedy(3000, 3, 17)
+    assert (g.records.numpy().view(np.uint32) == orc.episode_records(gfb, gln)).all()
 
 
 def test_rollout_host_chunked(r48, orc):

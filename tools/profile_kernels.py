@@ -21,6 +21,16 @@ def main():
     torch.cuda.set_device(0)
     L = r48._native.lib()
     stream = torch.cuda.current_stream().cuda_stream
+    if a.which == "quick":
+        # 2 rollout launches at 2^22 and 2^24, 4 step launches at 2^20 (rotating windows), 2 at 2^23
+        for lg in (22, 24):
+            buf = r48.RolloutBuffers(1 << lg)
+            for i in range(2):
+                r48.random_rollouts(1 << lg, seed=2048 + i, buffers=buf, with_stats=False)
+            torch.cuda.synchronize()
+            st = int(buf.lengths.to(torch.int64).sum().item())
+            print("rollout 2^%d env_steps %d" % (lg, st))
+            buf = None
     if a.which in ("rollout", "all"):
         n = 1 << a.rollout_log2
         buf = r48.RolloutBuffers(n)
@@ -28,7 +38,7 @@ def main():
             r48.random_rollouts(n, seed=2048 + i, buffers=buf)
         torch.cuda.synchronize()
         print("rollout", r48.EpisodeStats(buf.stats).summary())
-    if a.which in ("step", "afterstates", "all"):
+    if a.which in ("step", "afterstates", "all", "quick"):
         n = 1 << 23
         env = r48.BatchedGame(n, seed=2048)
         for _ in range(64):
@@ -39,7 +49,7 @@ def main():
         rw = torch.empty(n, dtype=torch.int32, device="cuda")
         dn = torch.empty(n, dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
-    if a.which in ("step", "all"):
+    if a.which in ("step", "all", "quick"):
         m = 1 << 20
         for i in range(a.reps + 5):          # PROFILE_STEP_1M launches (rotating 1M windows)
             o = (i % 8) * m

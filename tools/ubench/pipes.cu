@@ -8,8 +8,8 @@
 #define ITERS 4096
 #define NCHAIN 8
 
-enum Op { LOP3, SHF_R, SHL_IMAD, PRMT, IADD3, IMAD, IMAD_HI, IMAD_WIDE, ISETP_SEL, POPC, LEA, VIMNMX, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_SHF_IMADSHL, LDS_NOCONF, LDS_RANDOM, IADD_IMAD, MIX_LOP_WIDE, MIX_IMM, MIX3, MIX_2TO1, NOPS };
-const char* names[] = {"LOP3","SHF.R","IMAD.SHL(mul 16)","PRMT","IADD3","IMAD","IMAD.HI.U32","IMAD.WIDE.U32","ISETP+SEL","POPC","LEA","VIMNMX","mix LOP3+IMAD 1:1","mix LOP3+IMAD.HI 1:1","mix SHF+IMAD.SHL 1:1","LDS no conflict","LDS random u16 idx","mad.lo x*1+y","mix LOP3+IMAD.WIDE 1:1","mix LOP3(imm)+IMAD(imm) 1:1","mix LOP3+IMAD+PRMT+IMAD","mix LOP3:IMAD 2:1"};
+enum Op { LOP3, SHF_R, SHL_IMAD, PRMT, IADD3, IMAD, IMAD_HI, IMAD_WIDE, ISETP_SEL, POPC, LEA, VIMNMX, MIX_LOP_IMAD, MIX_LOP_IMADHI, MIX_SHF_IMADSHL, LDS_NOCONF, LDS_RANDOM, IADD_IMAD, MIX_LOP_WIDE, MIX_IMM, MIX3, MIX_2TO1, LOP3_IMM, IMAD_IMM, MIX_IMM_2TO1, MIX_IMM_3TO1, MIX_IMM_5TO3, MIX_IMM_WIDE_3TO1, MIX_IMM_LDS, NOPS };
+const char* names[] = {"LOP3","SHF.R","IMAD.SHL(mul 16)","PRMT","IADD3","IMAD","IMAD.HI.U32","IMAD.WIDE.U32","ISETP+SEL","POPC","LEA","VIMNMX","mix LOP3+IMAD 1:1","mix LOP3+IMAD.HI 1:1","mix SHF+IMAD.SHL 1:1","LDS no conflict","LDS random u16 idx","mad.lo x*1+y","mix LOP3+IMAD.WIDE 1:1","mix LOP3(imm)+IMAD(imm) 1:1","mix LOP3+IMAD+PRMT+IMAD","mix LOP3:IMAD 2:1","LOP3 (imm operands)","IMAD (imm operands)","mix LOP3:IMAD imm 2:1","mix LOP3:IMAD imm 3:1","mix LOP3:IMAD imm 5:3","mix LOP3(imm):IMAD.WIDE 3:1","mix LOP3:IMAD imm 1:1 + 1 LDS per 16"};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long long* cycles)
@@ -48,6 +48,13 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, long lon
             if (OP == MIX_IMM) { if (c & 1) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); }
             if (OP == MIX3) { if ((c & 3) == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else if ((c & 3) == 2) asm volatile("prmt.b32 %0, %0, %1, 0x2301;" : "+r"(x[c]) : "r"(y)); else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); }
             if (OP == MIX_2TO1) { if ((c % 3) != 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[c]) : "r"(y), "r"(z)); }
+            if (OP == LOP3_IMM) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c]));
+            if (OP == IMAD_IMM) asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c]));
+            if (OP == MIX_IMM_2TO1) { if ((c % 3) != 2) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); }
+            if (OP == MIX_IMM_3TO1) { if ((c & 3) != 3) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); }
+            if (OP == MIX_IMM_5TO3) { if ((c & 7) < 5) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); }
+            if (OP == MIX_IMM_WIDE_3TO1) { if ((c & 3) != 3) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else { uint64_t p; asm volatile("mul.wide.u32 %0, %1, 0x9E3779B1;" : "=l"(p) : "r"(x[c])); x[c] = (uint32_t)(p >> 32) ^ (uint32_t)p; } }
+            if (OP == MIX_IMM_LDS) { if (c & 1) asm volatile("lop3.b32 %0, %0, 0x0f0f0f0f, 0x12345678, 0x96;" : "+r"(x[c])); else asm volatile("mad.lo.u32 %0, %0, 0x9E3779B1, 0x7F4A7C15;" : "+r"(x[c])); if (c == 0 && (it & 1) == 0) { uint32_t a = sbase + (threadIdx.x & 31) * 4 + (x[1] & 0x7f00); uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); x[7] ^= v; } }
             if (OP == MIX_LOP_WIDE) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(y), "r"(z)); else { uint64_t p; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x[c]), "r"(y)); x[c] = (uint32_t)(p >> 32) + (uint32_t)p; } }
         }
     }
@@ -85,5 +92,6 @@ int main()
     run<ISETP_SEL>(out, cyc, sms, 0); run<POPC>(out, cyc, sms, 0); run<LEA>(out, cyc, sms, 0); run<VIMNMX>(out, cyc, sms, 0);
     run<MIX_LOP_IMAD>(out, cyc, sms, 0); run<MIX_LOP_IMADHI>(out, cyc, sms, 0); run<MIX_SHF_IMADSHL>(out, cyc, sms, 0);
     run<LDS_NOCONF>(out, cyc, sms, 0); run<LDS_RANDOM>(out, cyc, sms, 0); run<IADD_IMAD>(out, cyc, sms, 0); run<MIX_LOP_WIDE>(out, cyc, sms, 0); run<MIX_IMM>(out, cyc, sms, 0); run<MIX3>(out, cyc, sms, 0); run<MIX_2TO1>(out, cyc, sms, 0);
+    run<LOP3_IMM>(out, cyc, sms, 0); run<IMAD_IMM>(out, cyc, sms, 0); run<MIX_IMM_2TO1>(out, cyc, sms, 0); run<MIX_IMM_3TO1>(out, cyc, sms, 0); run<MIX_IMM_5TO3>(out, cyc, sms, 0); run<MIX_IMM_WIDE_3TO1>(out, cyc, sms, 0); run<MIX_IMM_LDS>(out, cyc, sms, 0);
     return 0;
 }
