@@ -5,7 +5,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]                 (N = 1)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W        (N > 1, one rank per GPU)
-    python bench.py --impl reference [...]                               (CPU arm)
+    python bench.py --impl reference [...]                               (CPU arm: the unmodified reference)
 
 Metric (BASELINE.json): 2048 env-steps/sec of fused random-policy rollouts.  One "step" of the
 benchmark = one pass of the hot path over one batch: every rank plays `--boards-per-gpu`
@@ -13,12 +13,20 @@ episodes (default 2^26 = config 5's per-GPU shard; 2^29 in total at 8 GPUs) from
 over in the fused kernel, reduces them to the statistics vector and, for N > 1, all-reduces
 that vector over NCCL.  value = env-steps of all ranks / device time (max over ranks).
 
-The JSON line also carries: `e2e` (same metric through the host-buffer C-ABI entry point with
-the per-episode results copied back to pinned host memory inside the timed region), `roofline`
-(fused rollout kernel vs the integer-issue bound, as north_star prescribes for it),
-`roofline_hbm` + `kernels` (single-step kernel at 1M boards -- config 2 -- and afterstates at 8M
-boards -- config 4 -- vs the measured HBM copy peak), `cpu_baseline` (the Python port of the
-reference timed on this box's host cores) and `clocks`.
+The JSON line also carries:
+  e2e            the same metric through the host-buffer C-ABI entry point (r48_rollout_host_ex)
+                 with one packed record per episode (score, length) + the statistics vector copied
+                 to pinned host memory inside the timed region; `e2e_modes` adds the 12-byte
+                 full-board records and the statistics-only form
+  stats_digest   sha256 of the all-reduced statistics of ONE fixed job (2^22 episodes, seed 2048,
+                 ids 0..2^22-1) sharded over the N ranks; rank 0 also plays the whole job alone and
+                 asserts the two vectors are equal -- the same digest must appear at N = 1, 2, 4, 8
+  roofline       fused rollout kernel vs the integer-issue bound (north_star's bound for it)
+  roofline_hbm / kernels   single-step kernel at 1M boards (config 2) with the same-harness
+                 22-byte copy ceiling, afterstates at 8M boards (config 4), env_step, the
+                 transition ring -- vs the measured HBM copy peak
+  cpu_baseline   the unmodified reference (oracle/_ref, byte-compiled by oracle/build_ref.py)
+                 timed on this box's host cores; falls back to the Python port if that is absent
 """
 import argparse
 import json
@@ -39,11 +47,18 @@ SEED = 2048
 
 # ---------------------------------------------------------------------- CPU arms (oracle/ is allowed here only)
 
-def cpu_python_port(episodes, cores):
-    """The reference's own algorithm and data structures (oracle/pyport.py), all host cores."""
-    from oracle import pyport
-    steps, dt = pyport.timed_rollouts(episodes, cores)
-    return steps, dt
+def cpu_reference(episodes, cores):
+    """The reference's own CPU path over all host cores: the unmodified reference from oracle/_ref
+    when it was built (kind "reference"), else oracle/pyport.py (kind "port")."""
+    from oracle import refarm
+    return refarm.timed_rollouts(episodes, cores)            # (steps, seconds, kind)
+
+
+REF_WHAT = {
+    "reference": "the unmodified reference (game/GameClient.py + control/rand.py + main.play), byte-compiled into "
+                 "oracle/_ref by oracle/build_ref.py: random.seed(s); Game(); play(game, 'rand')",
+    "port": "oracle/pyport.py: Python restatement with the reference's data structures (oracle/_ref was not built)",
+}
 
 
 def cpu_c_port(episodes, threads):
@@ -63,18 +78,18 @@ def host_cores():
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (Python port of
-    GameClient.py + rand.py + main.play; the reference itself is Python and cannot travel to
-    the GPU box), all host cores, same metric/unit/config as our arm.  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path, all host cores, same
+    metric/unit/config as our arm.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     cores = host_cores()
     per_step = args.ref_episodes_per_core * cores
+    kind = "port"
     for _ in range(args.warmup):
-        cpu_python_port(max(cores, per_step // 8), cores)
+        cpu_reference(max(cores, per_step // 8), cores)
     total_steps, total_dt = 0, 0.0
     for _ in range(args.steps):
-        s, dt = cpu_python_port(per_step, cores)
+        s, dt, kind = cpu_reference(per_step, cores)
         total_steps += s
         total_dt += dt
     value = total_steps / total_dt
@@ -86,9 +101,8 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "python int",
         "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "what": "oracle/pyport.py: Python restatement of game/GameClient.py + control/rand.py "
-                                 "+ main.play with the reference's data structures (lists, deepcopy, random)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "what": REF_WHAT[kind]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "episodes_per_sec": per_step * args.steps / total_dt,
     }
@@ -176,8 +190,8 @@ def measured_peaks():
 
 
 def rollout_issue_profile():
-    """Warp-instructions the rollout kernel issues per 32 env-steps, measured once by ncu
-    (profiles/rollout_issue.json, from smsp__inst_executed.sum of a 2^22-episode launch)."""
+    """Warp-instructions the rollout kernel issues per 32 env-steps, measured by ncu
+    (profiles/rollout_issue.json: smsp__inst_executed.sum of launches at several sizes)."""
     path = os.path.join(ROOT, "profiles", "rollout_issue.json")
     if os.path.exists(path):
         return json.load(open(path))
@@ -190,7 +204,7 @@ def ncu_traffic(profile, index=0):
     path = os.path.join(ROOT, "profiles", profile)
     try:
         d = json.load(open(path))[index]
-    except (OSError, IndexError, ValueError):
+    except (OSError, IndexError, ValueError, KeyError):
         return None
     total = 0.0
     for key, val in d.items():
@@ -239,6 +253,14 @@ def time_graph(torch, fn, launches, replays=10):
     return start.elapsed_time(end) / (replays * launches)
 
 
+def hbm_roofline(alg_bytes, ms, hbm_peak, traffic=None, **extra):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+         "algorithmic_bytes_per_launch": alg_bytes, "traffic": traffic}
+    r.update(extra)
+    return r
+
+
 def bench_step_kernel(torch, r48, hbm_peak):
     """Config 2: 1M boards, one batched step per call, host-supplied actions already in HBM.
     Eight rotating buffer sets (8 x 22 MB = 176 MB > 126 MB L2) so every launch reads HBM."""
@@ -262,25 +284,38 @@ def bench_step_kernel(torch, r48, hbm_peak):
     def launch(i):
         o = (i % sets) * n
         r48._native.check(L.r48_step(pb + 8 * o, pa + o, po + 8 * o, pr + 4 * o, pd + o, n, SEED, o, 64, 0, None, cur()))
+
+    def copy(i):
+        o = (i % sets) * n
+        r48._native.check(L.r48_debug_copy22(pb + 8 * o, pa + o, po + 8 * o, pr + 4 * o, pd + o, n, cur()))
     ms = time_graph(torch, launch, 64)
+    ms_copy = time_graph(torch, copy, 64)
     alg_bytes = 22 * n
-    gbs = alg_bytes / (ms * 1e-3) / 1e9
     res = {"workload": "config 2: 2^20 boards, one step per call, actions in HBM, 8 rotating buffer sets (176 MB > L2), "
                        "64 launches captured in a CUDA graph, timed with CUDA events over 10 replays",
            "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
-           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                        "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_step_ncu.json", 0),
-                        "traffic_note": "ncu, one 2^20-board launch: the 9.7 MB read is the input; the 13.6 MB of "
-                                        "outputs is still in L2 when the kernel ends (8M-board launch: 136 MB of "
-                                        "176 MB algorithmic)"}}
-    # the same kernel on one 16M-board launch (352 MB): launch latency amortised
+           "roofline": hbm_roofline(alg_bytes, ms, hbm_peak, ncu_traffic("r02_step_ncu.json", 0),
+                                    traffic_note="ncu, one 2^20-board launch: most of the 13.6 MB of outputs is still in "
+                                                 "L2 when the kernel ends"),
+           # what 100 % means for a launch of this shape: the same 22 B per board moved by a kernel that
+           # computes nothing, in the same 64-launch graph
+           "copy_ceiling": {"kernel": "r48::copy22_kernel", "us_per_launch": ms_copy * 1e3,
+                            "GBps": alg_bytes / (ms_copy * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": alg_bytes / (ms_copy * 1e-3) / 1e9 / hbm_peak,
+                            "step_vs_copy": ms_copy / ms}}
+    # the same kernel on one 8M-board launch (176 MB): launch latency amortised
     nbig = n * sets
     def launch_big(i):
         r48._native.check(L.r48_step(pb, pa, po, pr, pd, nbig, SEED, 0, 64, 0, None, cur()))
+    def copy_big(i):
+        r48._native.check(L.r48_debug_copy22(pb, pa, po, pr, pd, nbig, cur()))
     ms_big = time_graph(torch, launch_big, 8)
+    ms_copy_big = time_graph(torch, copy_big, 8)
     gbs_big = 22 * nbig / (ms_big * 1e-3) / 1e9
     res["at_8M_boards"] = {"us_per_launch": ms_big * 1e3, "GBps": gbs_big, "frac": gbs_big / hbm_peak,
-                           "board_steps_per_sec": nbig / (ms_big * 1e-3)}
+                           "board_steps_per_sec": nbig / (ms_big * 1e-3),
+                           "copy_ceiling_us": ms_copy_big * 1e3,
+                           "copy_ceiling_frac_of_hbm_peak": 22 * nbig / (ms_copy_big * 1e-3) / 1e9 / hbm_peak}
     # size sweep (1M boards is launch/staging-latency sized); windows rotate through the 8M buffer
     sweep = {}
     for lg in (16, 18, 19, 20, 21, 22, 23):
@@ -292,6 +327,18 @@ def bench_step_kernel(torch, r48, hbm_peak):
         t = time_graph(torch, launch_m, max(8, min(64, wins)))
         sweep["2^%d" % lg] = {"us": t * 1e3, "GBps": 22 * m / (t * 1e-3) / 1e9}
     res["size_sweep"] = sweep
+    # the zero-copy Python call a DQN loop makes (BatchedGame.step, device tensors): launch path included
+    env1 = r48.BatchedGame(n, seed=SEED)
+    env1.boards.copy_(boards_in[:n])
+    a1 = actions[:n].contiguous()
+    for _ in range(20):
+        env1.step(a1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        env1.step(a1)
+    torch.cuda.synchronize()
+    res["python_call_us"] = (time.perf_counter() - t0) / 200 * 1e6
     # end to end through the host-buffer entry point (pinned host memory, copies inside)
     h_in = boards_in[:n].cpu().pin_memory()
     h_act = actions[:n].cpu().pin_memory()
@@ -315,9 +362,10 @@ def bench_step_kernel(torch, r48, hbm_peak):
 
 def bench_env_step_kernel(torch, r48, hbm_peak):
     """policy-in-the-loop step -- per-env counters, auto-reset, float32 readout fused
-    into the epilogue.  2^20 envs, 8 rotating env sets (8 x 102 MB); actions already in HBM."""
+    into the epilogue.  2^20 envs, 8 rotating env sets (8 x 102 MB); actions already in HBM.  Second
+    figure: the same call with the transition-ring append fused in (8(f).4)."""
     n, sets = 1 << 20, 8
-    envs = [r48.BatchedGame(n, seed=SEED + s, board_base=s * n) for s in range(sets)]
+    envs = [r48.BatchedGame(n, seed=SEED + s, board_base=s * n, id_stride=sets * n) for s in range(sets)]
     acts = [torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8) for _ in range(sets)]
     for e, a in zip(envs, acts):
         for _ in range(48):
@@ -327,12 +375,53 @@ def bench_env_step_kernel(torch, r48, hbm_peak):
         envs[i % sets].env_step(acts[i % sets])
     ms = time_graph(torch, launch, 32)
     alg_bytes = 102 * n          # board 8+8, action 1, steps 4+4, episodes 4+4, reward 4, done 1, obs 64
-    gbs = alg_bytes / (ms * 1e-3) / 1e9
-    return {"workload": "8(f).1: 2^20 envs, Game.step with per-env counters + auto-reset + fused float32 [n,4,4] "
-                        "readout, 8 rotating env sets",
-            "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_env_ncu.json", 0)}}
+    res = {"workload": "8(f).1: 2^20 envs, Game.step with per-env counters + auto-reset + fused float32 [n,4,4] "
+                       "readout, 8 rotating env sets",
+           "us_per_launch": ms * 1e3, "board_steps_per_sec": n / (ms * 1e-3),
+           "roofline": hbm_roofline(alg_bytes, ms, hbm_peak, ncu_traffic("r02_env_ncu.json", 0))}
+    ring = r48.ReplayRing(1 << 24)                 # 16M slots x 22 B = 369 MB (> L2)
+
+    def launch_ring(i):
+        envs[i % sets].env_step(acts[i % sets], ring=ring)
+    ms_r = time_graph(torch, launch_ring, 32)
+    res["with_ring_append"] = {"us_per_launch": ms_r * 1e3,
+                               "roofline": hbm_roofline(124 * n, ms_r, hbm_peak, None,
+                                                        note="+22 B per env written to the ring (s, a, r, s', done)")}
+    return res
+
+
+def bench_ring(torch, r48, hbm_peak):
+    """the transition ring on its own.  append: 2^20 transitions per call into a ring of
+    2^24 slots (read 22 B + write 22 B per transition); sample: 2^20 distinct slots gathered per call
+    (random 32-byte sectors: the traffic is ~7x the algorithmic bytes by construction)."""
+    n, cap = 1 << 20, 1 << 24
+    ring = r48.ReplayRing(cap, seed=SEED)
+    src = [torch.randint(0, 1 << 62, (n,), device="cuda", dtype=torch.int64) for _ in range(2)]
+    a = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8)
+    rw = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for _ in range(17):
+        ring.store(src[0], a, rw, src[1], a)
+
+    def append(i):
+        ring.store(src[i & 1], a, rw, src[1 - (i & 1)], a)
+    ms_a = time_graph(torch, append, 32)
+    L = r48._native.lib()
+    out = ring.sample(n)                           # allocates nothing we keep; buffers for the timed loop:
+    bufs = {k: torch.empty_like(v) for k, v in out.items()}
+    st = lambda: torch.cuda.current_stream().cuda_stream
+
+    def sample(i):
+        r48._native.check(L.r48_ring_sample(ring._ref(), n, SEED, i, 0, bufs["index"].data_ptr(), bufs["state"].data_ptr(),
+                                            bufs["action"].data_ptr(), bufs["reward"].data_ptr(), bufs["next_state"].data_ptr(),
+                                            bufs["done"].data_ptr(), None, None, 0, st()))
+    ms_s = time_graph(torch, sample, 16)
+    return {"workload": "8(f).4: ring of 2^24 transitions (369 MB), 2^20 per call",
+            "append": {"us_per_launch": ms_a * 1e3, "transitions_per_sec": n / (ms_a * 1e-3),
+                       "roofline": hbm_roofline(44 * n, ms_a, hbm_peak, None)},
+            "sample": {"us_per_launch": ms_s * 1e3, "transitions_per_sec": n / (ms_s * 1e-3),
+                       "roofline": hbm_roofline(52 * n, ms_s, hbm_peak, None,
+                                                note="22 B gathered + 30 B written (incl. the int64 slot index) per "
+                                                     "sample; every gathered field costs a 32-byte sector")}}
 
 
 def bench_afterstates_kernel(torch, r48, hbm_peak):
@@ -353,11 +442,44 @@ def bench_afterstates_kernel(torch, r48, hbm_peak):
         r48._native.check(L.r48_afterstates(*ptrs, n, 0, torch.cuda.current_stream().cuda_stream))
     ms = time_graph(torch, launch, 8)
     alg_bytes = 58 * n
-    gbs = alg_bytes / (ms * 1e-3) / 1e9
     return {"workload": "config 4: 2^23 boards x 4 afterstates + valid mask + done, 464 MB per launch (> L2)",
             "us_per_launch": ms * 1e3, "boards_per_sec": n / (ms * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": ncu_traffic("r01_afterstates_ncu.json", 0)}}
+            "roofline": hbm_roofline(alg_bytes, ms, hbm_peak, ncu_traffic("r02_afterstates_ncu.json", 0))}
+
+
+def bench_game_adapter(r48):
+    """Config 1 through the new backend: the drop-in `Game` (a batch of ONE board, every transition on
+    the GPU, the reference's draws injected) playing seeded episodes.  Launch- and sync-bound by
+    construction: this is the compatibility surface, not the data path."""
+    import random
+    steps, t0 = 0, time.perf_counter()
+    for s in range(3):
+        random.seed(s)
+        g = r48.Game()
+        over = False
+        while not over:
+            _, _, over = g.step(r48.Rand.random_action(g.state_matrix))
+            steps += 1
+    dt = time.perf_counter() - t0
+    return {"workload": "config 1 through rein48_b200.Game (rng='python'): seeds 0..2, played to game over",
+            "env_steps": steps, "env_steps_per_sec": steps / dt, "us_per_step": dt / steps * 1e6,
+            "note": "3 kernel launches + 3 device->host reads per step; the reference's own Python Game.step is "
+                    "~27 us (37 k steps/s per core)"}
+
+
+def stats_digest(torch, dist, r48, world, rank, dev):
+    """ONE fixed job -- 2^22 episodes, seed 2048, ids 0..2^22-1 -- sharded over the ranks and all-reduced;
+    rank 0 replays the whole job alone and requires the same vector.  Returns (sha256 hex, equal)."""
+    import hashlib
+    n_total = 1 << 22
+    res = r48.sharded_rollouts(n_total, seed=SEED, device=dev)
+    reduced = res.stats.clone()
+    equal = True
+    if rank == 0:
+        whole = r48.random_rollouts(n_total, seed=SEED, device=dev).stats
+        equal = bool((whole == reduced).all().item())
+    digest = hashlib.sha256(reduced.cpu().numpy().tobytes()).hexdigest()
+    return digest, equal
 
 
 def run_ours(args):
@@ -372,12 +494,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         episodes = args.cpu_episodes_per_core * cores
-        steps, dt = cpu_python_port(episodes, cores)
-        cpu_baseline = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        steps, dt, kind = cpu_reference(episodes, cores)
+        cpu_baseline = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": kind,
                         "sample": "%d seeded episodes (seeds 0..%d) of the same workload, multiprocessing.Pool(%d), "
                                   "%.1f s" % (episodes, episodes - 1, cores, dt),
-                        "what": "oracle/pyport.py (Python restatement with the reference's lists/deepcopy/random)",
-                        "episodes_per_sec": episodes / dt}
+                        "what": REF_WHAT[kind], "episodes_per_sec": episodes / dt}
         c_eps = 60000 * cores
         steps, dt = cpu_c_port(c_eps, cores)
         cpu_c = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -395,6 +516,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     r48._native.check(r48._native.lib().r48_init(local_rank))
+
+    # N > 1 parity, visible in the line: the same digest at every N
+    digest, digest_ok = stats_digest(torch, dist, r48, world, rank, dev)
+    if not digest_ok:
+        raise SystemExit("the statistics of the job sharded over %d ranks differ from the single-GPU run" % world)
 
     n = args.boards_per_gpu
     base = rank * n
@@ -454,29 +580,40 @@ def run_ours(args):
     env_steps = st.steps
     episodes = st.episodes
     value = env_steps / elapsed_s
+    buf = None
+    torch.cuda.empty_cache()
 
-    # ---- e2e: the public host-buffer API, per-episode results copied to pinned host memory
-    host_out = r48.RolloutResult(torch.empty(n, dtype=torch.int64).pin_memory(),
-                                 torch.empty(n, dtype=torch.int32).pin_memory(),
-                                 torch.empty(r48.STATS_WORDS, dtype=torch.int64).pin_memory())
-    r48.random_rollouts_host(n, seed=SEED + 2000, device=local_rank, board_base=base, out=host_out)
-    e2e_steps_n = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_env_steps = 0
-    for i in range(e2e_steps_n):
-        r48.random_rollouts_host(n, seed=SEED + i, device=local_rank, board_base=base, out=host_out)
-        e2e_env_steps += int(host_out.stats[r48.stats.SUM_LEN])
-    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    e2e_cnt = torch.tensor([e2e_env_steps], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_cnt, op=dist.ReduceOp.SUM)
-    e2e = {"value": float(e2e_cnt.item()) / float(e2e_dt.item()), "unit": UNIT,
-           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": (12 * n + 8 * r48.STATS_WORDS) * world,
-           "steps": e2e_steps_n, "api": "rein48_b200.random_rollouts_host -> r48_rollout_host (C ABI, host buffers)",
-           "note": "the path has no per-step host input (episodes are generated from (seed, board id)); the timed "
-                   "region includes launch, kernels, D2H of final boards + lengths + statistics and the sync"}
+    # ---- e2e: the public host-buffer API; results land in pinned host memory inside the timed region
+    def e2e_leg(make_out, records, d2h_per_episode):
+        out = make_out()
+        r48.random_rollouts_host(n, seed=SEED + 2000, device=local_rank, board_base=base, out=out, records=records)
+        reps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        steps_done = 0
+        for i in range(reps):
+            r48.random_rollouts_host(n, seed=SEED + i, device=local_rank, board_base=base, out=out, records=records)
+            steps_done += int(out.stats[r48.stats.SUM_LEN])
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([steps_done], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        return {"value": float(cnt.item()) / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": (d2h_per_episode * n + 8 * r48.STATS_WORDS) * world, "steps": reps,
+                "ms_per_step": float(dt.item()) / reps * 1e3}
+
+    pin = lambda *shape_dtype: torch.empty(shape_dtype[0], dtype=shape_dtype[1]).pin_memory()
+    e2e = e2e_leg(lambda: r48.HostRecords(pin(n, torch.int32), pin(r48.STATS_WORDS, torch.int64)), True, 4)
+    e2e.update({
+        "api": "rein48_b200.random_rollouts_host(records=True) -> r48_rollout_host_ex (C ABI, host buffers)",
+        "payload": "one uint32 per episode (score / 2 << 13 | min(length, 8191): what main.py:48 prints per game, plus "
+                   "the episode length) + the 33 KB statistics vector",
+        "note": "the path has no per-step host input (episodes are generated from (seed, board id)); the timed region "
+                "includes launches, kernels, the D2H copies and the final synchronise"})
+    e2e_full = e2e_leg(lambda: r48.RolloutResult(pin(n, torch.int64), pin(n, torch.int32), pin(r48.STATS_WORDS, torch.int64)),
+                       False, 12)
+    e2e_full["payload"] = "final board (8 B) + length (4 B) per episode + statistics: round 1's e2e payload"
 
     if rank != 0:
         if world > 1:
@@ -501,31 +638,37 @@ def run_ours(args):
         peak = 148 * 4 * sm_mhz * 1e6 * 32 / w
         roofline.update({"peak": peak, "frac": per_gpu_rate / peak,
                          "warp_instr_per_32_steps": w, "instr_source": prof.get("source"),
+                         "instr_by_launch_size": prof.get("by_launch_size"),
                          "ipc_per_sm_implied": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6),
                          "peak_formula": "148 SMs x 4 schedulers x sm_mhz (median under load) x 32 lanes / "
                                          "warp-instructions per 32 env-steps (ncu); frac = issue-slot utilisation",
-                         "measured_issue_ceiling_ipc_per_sm": 2.78,
-                         "frac_of_measured_ceiling": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6) / 2.78,
-                         "ceiling_note": "tools/ubench/pipes.cu: a synthetic 1:1 LOP3/IMAD stream (8 independent "
-                                         "chains per thread, 32 warps/SM) sustains 2.77-2.78 warp-instr/cycle/SM on "
-                                         "this chip, single-pipe integer streams 1.98 -- the nominal 4/cycle is not "
-                                         "reachable with integer work",
+                         "issue_note": prof.get("issue_note"),
                          "traffic": prof.get("dram_bytes_per_launch"),
-                         "traffic_note": "dram bytes of the profiled 2^22-episode launch (most of its 50 MB of "
-                                         "outputs is still in L2 when the kernel ends)"})
+                         "traffic_note": prof.get("traffic_note")})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_s * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "clocks": clocks, "e2e": e2e, "e2e_modes": {"records_4B": e2e["value"], "full_boards_12B": e2e_full},
+        "gpu_launches": 2 * args.steps,
+        "stats_digest": digest, "stats_digest_job": "2^22 episodes, seed %d, ids 0..2^22-1, sharded over %d rank(s); equal "
+                                                    "to rank 0's single-GPU replay: %s" % (SEED, world, digest_ok),
         "episodes_per_sec": episodes / elapsed_s, "env_steps": env_steps, "episodes": episodes,
         "mean_episode_length": st.mean_length, "mean_score": st.mean_score, "max_tile": st.max_tile,
         "kernel_ms": {"rollout": rollout_ms, "episode_stats": stats_ms, "allreduce": reduce_ms},
         "roofline": roofline,
         "hbm_peak": {"GBps": hbm_peak, "source": peak_src},
     }
+    if world == 1:
+        # statistics-only e2e (33 KB per step to the host)
+        sto = pin(r48.STATS_WORDS, torch.int64)
+        L.r48_rollout_host_ex(n, SEED, base, 0, None, None, None, sto.data_ptr(), local_rank)
+        t0 = time.perf_counter()
+        r48._native.check(L.r48_rollout_host_ex(n, SEED + 1, base, 0, None, None, None, sto.data_ptr(), local_rank))
+        dt = time.perf_counter() - t0
+        line["e2e_modes"]["stats_only"] = {"value": int(sto[r48.stats.SUM_LEN]) / dt, "unit": UNIT,
+                                           "d2h_bytes_per_step": 8 * r48.STATS_WORDS, "ms_per_step": dt * 1e3}
     if world == 1 and not args.quick:
-        buf = None
         torch.cuda.empty_cache()
         # config 3 exactly: 2^24 episodes on one GPU
         n3 = 1 << 24
@@ -564,10 +707,15 @@ def run_ours(args):
         tr = None
         torch.cuda.empty_cache()
         ks = bench_step_kernel(torch, r48, hbm_peak)
+        torch.cuda.empty_cache()
         ka = bench_afterstates_kernel(torch, r48, hbm_peak)
+        torch.cuda.empty_cache()
         ke = bench_env_step_kernel(torch, r48, hbm_peak)
-        line["kernels"] = {"step_1M": ks, "afterstates_8M": ka, "env_step_1M": ke}
+        torch.cuda.empty_cache()
+        kr = bench_ring(torch, r48, hbm_peak)
+        line["kernels"] = {"step_1M": ks, "afterstates_8M": ka, "env_step_1M": ke, "ring": kr}
         line["roofline_hbm"] = dict(ks["roofline"], kernel="r48::step_kernel", peak_source=peak_src)
+        line["game_adapter"] = bench_game_adapter(r48)
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
         line["cpu_baseline_c"] = cpu_c

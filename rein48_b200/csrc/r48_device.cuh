@@ -56,12 +56,77 @@ __device__ __forceinline__ uint32_t smem_u32_pinned(const void *p)
     return r;
 }
 
+// These are volatile asm statements WITHOUT a "memory" clobber on purpose: volatile keeps them in
+// program order among themselves (load, ..., store of one trip), while a clobber would make the
+// compiler re-read every kernel parameter after each of them.
+__device__ __forceinline__ ulonglong2 ldg_u64x2(uint64_t addr)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ldg_u16(uint64_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void stg_u64x2(uint64_t addr, uint64_t x, uint64_t y)
+{
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(addr), "l"(x), "l"(y));
+}
+
+__device__ __forceinline__ void stg_u32x2(uint64_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(x), "r"(y));
+}
+
+__device__ __forceinline__ void stg_u16(uint64_t addr, uint32_t v)
+{
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"((uint16_t)v));
+}
+
 // volatile: must not move above the mbarrier wait that publishes the staged tables
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+__device__ __forceinline__ uint32_t lds_u32_at(const uint32_t *p)
+{
+    return lds_u32(smem_u32(p));
+}
+
+// Launch constants for a hot loop, pinned in registers.  ptxas re-reads kernel parameters from
+// the constant bank (LDC / LDCU) wherever it uses them -- ~9 issue slots per board in the step
+// kernel, which runs at the issue ceiling -- and it sees through PTX moves and self-shuffles.  What
+// it cannot fold is a value that came through shared memory: thread 0 parks the words of the
+// parameters there, and after the CTA barrier every thread reads the words back once.
+template <int N>
+struct PinnedWords {
+    uint32_t w[N];
+    // after the CTA barrier that follows the parking stores (sts_u32_at by one thread)
+    __device__ __forceinline__ void fetch(const uint32_t *slots)
+    {
+#pragma unroll
+        for (int t = 0; t < N; t++) w[t] = lds_u32_at(slots + t);
+    }
+    __device__ __forceinline__ uint64_t u64(int t) const { return ((uint64_t)w[t + 1] << 32) | w[t]; }
+};
+
+__device__ __forceinline__ void sts_u32_at(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v));
+}
+
+__device__ __forceinline__ void sts_u64_at(uint32_t *p, uint64_t v)
+{
+    sts_u32_at(p, (uint32_t)v);
+    sts_u32_at(p + 1, (uint32_t)(v >> 32));
 }
 
 // ------------------------------------------------------------------ Philox4x32-7
@@ -114,7 +179,7 @@ __device__ __forceinline__ uint32_t draw_word(uint64_t id, uint32_t tick, const 
 }
 
 // exponent of the spawned tile (2 for a "4", 1 for a "2") as v29 = exponent << 29 (see
-// place_tile_v29); 0 when nothing is spawned
+// spawn_tile); 0 when nothing is spawned
 __device__ __forceinline__ uint32_t spawn_v29(uint32_t a, bool changed)
 {
     const uint32_t v = (a * R48_VALUE_HASH < R48_SPAWN4_THRESHOLD) ? (2u << 29) : (1u << 29);
@@ -180,8 +245,13 @@ struct PhiloxLaunch {
     uint32_t r1_h0k;    // hi(M0*r0_n0) ^ k1[1]
     uint32_t r2_c3k;    // lo(M0*r0_n0) ^ k1[2]         (c3 entering round 2, key folded in)
     uint32_t word;      // tick & 3
+    uint32_t last_mul;  // M1 for words 0,1; M0 for words 2,3
+    uint32_t last_key;  // k0[6] for word 0, k1[6] for word 2
 };
 
+// WORD = tick & 3 as a compile-time constant (the host picks the kernel instantiation): the last
+// round is then two instructions; WORD < 0 selects by the launch constant P.word instead.
+template <int WORD>
 __device__ __forceinline__ uint32_t philox_launch_word(uint32_t id_lo, const PhiloxLaunch &P,
                                                        const PhiloxKeys &K)
 {
@@ -213,12 +283,18 @@ __device__ __forceinline__ uint32_t philox_launch_word(uint32_t id_lo, const Phi
             y3 = (uint32_t)p0c;
             y0 = m0; y2 = m2;
         }
-        // last round: one word (P.word is launch-uniform, so this is a uniform branch)
+        // last round: only the word the tick uses.  Words 0,1 come from M1 * c2, words 2,3 from
+        // M0 * c0; even words are the high half XOR a counter word XOR the key, odd words the low
+        // half.  The selectors are launch constants (three selects, one multiply, one XOR).
         constexpr int L = kPhiloxRounds - 1;
-        if (P.word == 0u) return __umulhi(R48_PHILOX_M1, y2) ^ y1 ^ K.k0[L];
-        if (P.word == 1u) return R48_PHILOX_M1 * y2;
-        if (P.word == 2u) return __umulhi(R48_PHILOX_M0, y0) ^ y3 ^ K.k1[L];
-        return R48_PHILOX_M0 * y0;
+        if (WORD == 0) return __umulhi(R48_PHILOX_M1, y2) ^ y1 ^ K.k0[L];
+        if (WORD == 1) return R48_PHILOX_M1 * y2;
+        if (WORD == 2) return __umulhi(R48_PHILOX_M0, y0) ^ y3 ^ K.k1[L];
+        if (WORD == 3) return R48_PHILOX_M0 * y0;
+        const bool upper = P.word >= 2u, odd = (P.word & 1u) != 0u;
+        const uint64_t pr = (uint64_t)(upper ? y0 : y2) * P.last_mul;
+        const uint32_t even_word = (uint32_t)(pr >> 32) ^ (upper ? y3 : y1) ^ P.last_key;
+        return odd ? (uint32_t)pr : even_word;
     }
 }
 
@@ -329,8 +405,8 @@ __device__ __forceinline__ void row_offsets(uint32_t w, const PipeConsts &pc, ui
 }
 
 // compress / merge-once / compress of one row, toward nibble 0 or toward nibble 3; all in
-// registers (no local array), out of line: it runs only for rows outside the table
-__device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
+// registers (no local array).  It runs only for rows outside the table.
+__device__ __forceinline__ uint32_t slow_row_inline(uint32_t r, bool toward_high)
 {
     if (toward_high) r = ((r & 0xFu) << 12) | ((r & 0xF0u) << 4) | ((r >> 4) & 0xF0u) | ((r >> 12) & 0xFu);
     uint32_t packed = 0, n = 0;                     // non-empty cells, packed toward nibble 0
@@ -352,6 +428,12 @@ __device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
     return out;
 }
 
+// out of line, for the kernels whose cold paths would otherwise inline many copies
+__device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
+{
+    return slow_row_inline(r, toward_high);
+}
+
 // `lr` below is the shared-window byte address of the staged table (smem_u32)
 __device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool toward_high)
 {
@@ -360,33 +442,64 @@ __device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool towa
     return o | (o << 16);
 }
 
+// The table is staged in two parts: rows below kLrSplit (last cell below 256 -- nearly every row of
+// nearly every board) complete on one barrier, the rest on a second one, so that a launch starts
+// looking rows up when 128 KB of the 224 KB have arrived.  One test on bit 15 of the row words
+// covers both rare cases -- "needs the second part" and "outside the table".
+constexpr uint32_t kLrSplit = 0x8000u;
+
 // GUARD = false skips the range test: only for callers that can PROVE every row is in the table
-// (the rollout kernel: a board whose tiles sum to less than 16384 has no 16384 tile).
-template <bool GUARD = true>
-__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, bool toward_high, uint32_t lr,
-                                        const PipeConsts &pc)
+// (the rollout kernel: a board whose tiles sum to less than 16384 has no 16384 tile) and that have
+// waited for both parts.  `need_high` is called (once per board at most) before any row >= kLrSplit
+// is looked up.
+// `pk` = the PRMT selector that re-packs two looked-up rows into a word: 0x5410 takes the low
+// halves (LEFT results), 0x7632 the high halves (RIGHT results).
+__device__ __forceinline__ uint32_t pack_selector(bool toward_high) { return toward_high ? 0x7632u : 0x5410u; }
+// the same from an action code 0..3 (bit 0 = toward high) as one multiply-add
+__device__ __forceinline__ uint32_t pack_selector_of_action(uint32_t action) { return 0x5410u + 0x2222u * (action & 1u); }
+
+template <bool GUARD = true, typename NeedHigh>
+__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk, uint32_t lr,
+                                        const PipeConsts &pc, NeedHigh need_high)
 {
+    const bool toward_high = pk != 0x5410u;          // used on the cold exact path only
     uint32_t o0, o1, o2, o3;
-    // a row is outside the table iff its top three bits are set; OR-ing the words first is a
-    // conservative test (it may send a board to the exact path for nothing)
-    const uint32_t both = lo | hi;
-    if (!GUARD || __builtin_expect((both & (both << 1) & (both << 2) & 0x80008000u) == 0u, 1)) {
+    bool exact = false;
+    if (GUARD) {
+        const uint32_t both = lo | hi;
+        if (__builtin_expect((both & 0x80008000u) != 0u, 0)) {          // some row >= kLrSplit
+            need_high();
+            // a row is outside the table iff its top three bits are set; the OR of the words is a
+            // conservative test (it may send a board to the exact path for nothing)
+            exact = (both & (both << 1) & (both << 2) & 0x80008000u) != 0u;
+        }
+    }
+    if (!exact) {
         uint32_t a0, a1, a2, a3;
         row_offsets(lo, pc, a0, a1);
         row_offsets(hi, pc, a2, a3);
         o0 = lds_u32(lr + a0); o1 = lds_u32(lr + a1);
         o2 = lds_u32(lr + a2); o3 = lds_u32(lr + a3);
     } else {
-        const uint32_t r0 = lo & 0xFFFFu, r1 = lo >> 16, r2 = hi & 0xFFFFu, r3 = hi >> 16;
-        o0 = lr_lookup(lr, r0, toward_high); o1 = lr_lookup(lr, r1, toward_high);
-        o2 = lr_lookup(lr, r2, toward_high); o3 = lr_lookup(lr, r3, toward_high);
+        // exact path: one row at a time in a rolled loop, nothing out of line -- a CALL inside the
+        // caller's loop would make ptxas reload every launch constant after it, on the hot path too
+        const uint64_t board = ((uint64_t)hi << 32) | lo;
+        uint64_t moved = 0ull;
+#pragma unroll 1
+        for (uint32_t t = 0; t < 4u; t++) {
+            const uint32_t r = (uint32_t)(board >> (16u * t)) & 0xFFFFu;
+            uint32_t o;
+            if (r < kLrRows) o = (lds_u32(lr + 4u * lr_slot(r)) >> (toward_high ? 16u : 0u)) & 0xFFFFu;
+            else o = slow_row_inline(r, toward_high);
+            moved |= (uint64_t)o << (16u * t);
+        }
+        lo = (uint32_t)moved; hi = (uint32_t)(moved >> 32);
+        return;
     }
-    const uint32_t pk = toward_high ? 0x7632u : 0x5410u;
     lo = prmt(o0, o1, pk);
     hi = prmt(o2, o3, pk);
 }
 
-// Game.update_matrix on a board in its true orientation (transposes inside)
 
 // all four afterstates: LEFT/RIGHT share one lookup per row, UP/DOWN one per column
 template <bool GUARD = true>
@@ -480,13 +593,16 @@ __device__ __forceinline__ void place_tile_checked(uint32_t &lo, uint32_t &hi, c
     place_tile(lo, hi, b, k & 15u, k < b.n ? vexp : 0u);
 }
 
-// The same for vexp in {0,1,2} given as v29 = vexp << 29: the high half of
-// (1 << (4i+3)) * (vexp << 29) is vexp << 4i, so the insert is one IMAD.HI per word.
-__device__ __forceinline__ void place_tile_v29(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t k,
-                                               uint32_t v29)
+// Spawn from the tick's word `a` when `changed`: the tile goes into the k-th blank,
+// k = mulhi(a << 2, n).  With v29 = exponent << 29 the high half of (1 << (4i+3)) * v29 is
+// exponent << 4i, so the insert is one IMAD.HI per word (with the board as the 64-bit addend's
+// high half).  A shift of the one-hot mask plus predicated ORs was measured 4 % slower: the
+// predicated value computation issues whether or not it is needed.
+__device__ __forceinline__ void spawn_tile(uint32_t &lo, uint32_t &hi, const Blanks &b, uint32_t a, bool changed)
 {
     uint32_t sl, sh;
-    kth_blank(b, k, sl, sh);
+    kth_blank(b, __umulhi(a << 2, b.n), sl, sh);
+    const uint32_t v29 = spawn_v29(a, changed);
     lo += __umulhi(sl, v29);
     hi += __umulhi(sh, v29);
 }
@@ -582,19 +698,36 @@ __device__ __forceinline__ void pdl_wait()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// CLOBBER = false: for tables that are only ever read through lds_u32 (volatile asm, so already
+// ordered after this wait); without the "memory" clobber the compiler does not re-read kernel
+// parameters after a wait that sits inside a loop.
+template <bool CLOBBER = true>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    if (CLOBBER) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smem_u32(bar)),
+            "r"(parity)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smem_u32(bar)),
+            "r"(parity));
+    }
 }
 
 }  // namespace r48

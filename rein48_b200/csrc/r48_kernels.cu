@@ -26,6 +26,10 @@
 
 namespace r48 {
 
+#ifndef R48_AFTER_PREFETCH
+#define R48_AFTER_PREFETCH 1
+#endif
+
 constexpr int kThreads = 1024;                    // one CTA per SM (the table fills its shared memory)
 constexpr uint32_t kLeftBytes = 65536 * 2;        // reward-mode tables: LEFT rows (u16) ...
 constexpr uint32_t kMergeBytes = 65536;           // ... + merged exponents (u8)
@@ -85,26 +89,30 @@ struct Tables {
     PipeConsts pc;
 };
 
-// REWARD: [left u16 x 65536][merges u8 x 65536] (192 KB); otherwise [lr u32 x kLrRows] (224 KB)
+// REWARD: [left u16 x 65536][merges u8 x 65536] (192 KB); otherwise [lr u32 x kLrRows] (224 KB).
+// Two barriers: bar[0] completes when the first 128 KB are in (the whole LEFT table, or the LR
+// rows below kLrSplit), bar[1] when the rest is.
 template <bool REWARD>
 __device__ __forceinline__ void stage_tables(uint8_t *smem, const Tables &g, uint64_t *bar)
 {
-    if (threadIdx.x == 0) mbar_init(bar, 1);
+    constexpr uint32_t kFirst = REWARD ? kLeftBytes : kLrSplit * 4u;
+    constexpr uint32_t kTotal = REWARD ? kLeftBytes + kMergeBytes : kLrBytes;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     __syncthreads();
     if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar[0], kFirst);
+        mbar_expect_tx(&bar[1], kTotal - kFirst);
         if (REWARD) {
-            mbar_expect_tx(bar, kLeftBytes + kMergeBytes);
 #pragma unroll
             for (uint32_t off = 0; off < kLeftBytes; off += 32768u)
-                bulk_g2s(smem + off, (const uint8_t *)g.left + off, 32768u, bar);
+                bulk_g2s(smem + off, (const uint8_t *)g.left + off, 32768u, &bar[0]);
 #pragma unroll
             for (uint32_t off = 0; off < kMergeBytes; off += 32768u)
-                bulk_g2s(smem + kLeftBytes + off, g.merges + off, 32768u, bar);
+                bulk_g2s(smem + kLeftBytes + off, g.merges + off, 32768u, &bar[1]);
         } else {
-            mbar_expect_tx(bar, kLrBytes);
 #pragma unroll
             for (uint32_t off = 0; off < kLrBytes; off += 32768u)
-                bulk_g2s(smem + off, (const uint8_t *)g.lr + off, 32768u, bar);
+                bulk_g2s(smem + off, (const uint8_t *)g.lr + off, 32768u, off < kFirst ? &bar[0] : &bar[1]);
         }
     }
     // The tables never change after r48_init, so staging them does not depend on the previous
@@ -112,6 +120,17 @@ __device__ __forceinline__ void stage_tables(uint8_t *smem, const Tables &g, uin
     pdl_launch_dependents();
     pdl_wait();
 }
+
+// which parts of the table this thread has seen arrive
+template <bool REWARD>
+struct TableGate {
+    uint64_t *bar;
+    bool first, second;
+    // the reward-mode tables are read through plain pointers: their waits keep the memory clobber
+    __device__ __forceinline__ void need_first() { if (!first) { mbar_wait<REWARD>(&bar[0], 0); first = true; } }
+    __device__ __forceinline__ void need_second() { if (!second) { mbar_wait<REWARD>(&bar[1], 0); second = true; } }
+    __device__ __forceinline__ void need_all() { need_first(); need_second(); }     // also: never exit with a copy in flight
+};
 
 template <bool REWARD>
 constexpr uint32_t table_bytes() { return REWARD ? kLeftBytes + kMergeBytes : kLrBytes; }
@@ -202,26 +221,26 @@ struct StepParams {
 };
 
 // One board through Game.step.  `aw` = the tick's Philox word (or the injected k), `vw` = the
-// injected exponent.  An action byte > 3 (GameClient.py:254 raises there) sets `bad` and passes
-// the board through.
+// injected exponent.  Returns whether the board is FULL after the spawn; the caller evaluates
+// has_game_over for those (rare) boards -- it is symmetric under transposition, so it does not
+// matter that the test runs after the board has been put straight again.  An action byte > 3
+// moves nothing useful here; the callers detect it and pass the board through (illegal_action).
 //
 // The spawn counts blanks in the order of the move's axis, so for UP/DOWN it happens on the
 // transposed board, between the two transposes (nothing extra to compute); injected draws index
 // the reference's row-major blank list (GameClient.py:109-114), so there the board is transposed
-// back first.  has_game_over is symmetric under transposition and is evaluated wherever the board
-// happens to be, and only for boards that are full after the spawn.
+// back first.
 template <bool REWARD, bool INJECT>
-__device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
+__device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
                                          uint32_t vw, const uint8_t *smem, uint32_t lr, const PipeConsts &pc,
-                                         int32_t &reward, uint32_t &done, uint32_t &bad)
+                                         TableGate<REWARD> &gate, int32_t &reward)
 {
-    const uint32_t in_lo = lo, in_hi = hi;
     const bool vertical = is_vertical(action);
     if (vertical) transpose(lo, hi);
     const uint32_t olo = lo, ohi = hi;
     uint32_t rw = 0;
     if (REWARD) rows_l16<true>(lo, hi, is_toward_high(action), (const uint16_t *)smem, smem + kLeftBytes, rw);
-    else rows_lr(lo, hi, is_toward_high(action), lr, pc);
+    else rows_lr(lo, hi, pack_selector_of_action(action), lr, pc, [&] { gate.need_second(); });
     const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
     bool full;
     if (INJECT) {
@@ -231,142 +250,192 @@ __device__ __forceinline__ void step_one(uint32_t &lo, uint32_t &hi, uint32_t ac
         full = (any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u;
     } else {
         const Blanks b = count_blanks(lo, hi);
-        place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), spawn_v29(aw, changed));
+        spawn_tile(lo, hi, b, aw, changed);
         // full after the spawn <=> the moved board had no blank, or exactly one that was filled
         full = b.n == (changed ? 1u : 0u);
+        if (vertical) transpose(lo, hi);
     }
-    done = 0u;
-    if (full) done = no_equal_neighbours(lo, hi) ? 1u : 0u;
-    if (!INJECT && vertical) transpose(lo, hi);
     reward = REWARD ? (int32_t)rw : 0;
-    if (__builtin_expect(action > 3u, 0)) {
-        bad = 1u;
-        lo = in_lo; hi = in_hi; reward = 0;
-        done = game_over(lo, hi) ? 1u : 0u;
-    }
+    return full;
+}
+
+// GameClient.py:254 raises ValueError for an action it does not know; a batch cannot raise per
+// board, so the board is passed through with reward 0 and the caller's status word is flagged
+__device__ __forceinline__ void illegal_action(uint32_t &lo, uint32_t &hi, uint64_t input, int32_t &reward,
+                                               uint32_t &done)
+{
+    lo = (uint32_t)input; hi = (uint32_t)(input >> 32);
+    reward = 0;
+    done = game_over(lo, hi) ? 1u : 0u;
 }
 
 // Work split: every CTA owns one contiguous slice of the batch (equal slices, so all SMs finish
-// together even when a launch is only a few trips long -- 2^20 boards are 7 boards per thread),
-// and walks it in warp chunks: lane L takes units L and 32+L of a 64-unit chunk, both loads are
-// issued before any compute and the chunk of the NEXT trip is prefetched into L2 at the same
-// time, so that its loads find the data there instead of waiting on HBM.  Short slices (small
-// launches) use 32-unit chunks, one unit per lane, to spread over more warps.  VEC: a unit is a
-// PAIR of boards moved with 128-bit loads/stores (needs 16-byte aligned in/out, 8-byte reward,
-// 2-byte action/done), i.e. up to four boards per thread per trip; otherwise a unit is one board.
+// together even when a launch is only a few trips long -- 2^20 boards are 7 boards per thread);
+// a thread takes one unit per trip and the unit of its NEXT trip is prefetched into L2 while it
+// computes, so that the next loads find their data there instead of waiting on HBM.  VEC: a unit
+// is a PAIR of boards moved with 128-bit loads/stores (needs 16-byte aligned in/out, 8-byte
+// reward, 2-byte action/done); otherwise a unit is one board.  The loop is deliberately bare: the
+// kernel runs at the SM's integer issue ceiling, so every bookkeeping instruction per trip is a
+// fraction of a percent of its time (profiles/r02_step_budget.txt).
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <bool REWARD, bool INJECT, bool VEC>
+__device__ __forceinline__ void prefetch_l2_at(uint64_t global_addr)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(global_addr));
+}
+
+#ifndef R48_STEP_PREFETCH
+#define R48_STEP_PREFETCH 1
+#endif
+
+// WORD = tick & 3 (see philox_launch_word); injected-draw kernels ignore it
+template <bool REWARD, bool INJECT, bool VEC, int WORD>
 __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
-    stage_tables<REWARD>(smem, p.tables, &bar);
+    __shared__ uint64_t bar[2];
+    // the launch constants of the loop below, pinned in registers (see PinnedWords)
+    constexpr int kPinned = 2 * kPhiloxRounds + 4 + 10 + 2;
+    __shared__ uint32_t pin_slots[kPinned];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < kPhiloxRounds; r++) {
+            sts_u32_at(pin_slots + r, p.keys.k0[r]);
+            sts_u32_at(pin_slots + kPhiloxRounds + r, p.keys.k1[r]);
+        }
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 0, p.pl.r1_c1k);
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 1, p.pl.r1_h0k);
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 2, p.pl.r2_c3k);
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 3, p.id_lo);
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 4, (uint64_t)__cvta_generic_to_global(p.in));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 6, (uint64_t)__cvta_generic_to_global(p.action));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 8, (uint64_t)__cvta_generic_to_global(p.out));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 10, (uint64_t)__cvta_generic_to_global(p.reward));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 12, (uint64_t)__cvta_generic_to_global(p.done));
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 14, p.reward != nullptr ? 1u : 0u);
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 15, p.done != nullptr ? 1u : 0u);
+    }
+    stage_tables<REWARD>(smem, p.tables, bar);            // (its CTA barrier publishes pin_slots)
     const uint32_t lr = smem_u32_pinned(smem);
+    TableGate<REWARD> gate{bar, false, false};
+    PinnedWords<kPinned> pw;
+    pw.fetch(pin_slots);
 
-    bool ready = false;
     uint32_t bad = 0;
     const uint32_t units = VEC ? (p.n >> 1) : p.n;
-    const uint32_t per = ((units + gridDim.x - 1u) / gridDim.x + 31u) & ~31u;
+    const uint32_t per = ((units + gridDim.x - 1u) / gridDim.x + 31u) & ~31u;      // whole warps per slice
     const uint32_t begin = min(units, blockIdx.x * per), end = min(units, begin + per);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const bool dual = per > (uint32_t)kThreads;          // CTA-uniform: two units per lane per trip
-    const uint32_t chunk = dual ? 64u : 32u, trip = (kThreads / 32) * chunk;
+
+    PhiloxKeys keys;
+    PhiloxLaunch pl = p.pl;
+#pragma unroll
+    for (int r = 0; r < kPhiloxRounds; r++) { keys.k0[r] = pw.w[r]; keys.k1[r] = pw.w[kPhiloxRounds + r]; }
+    pl.r1_c1k = pw.w[2 * kPhiloxRounds + 0]; pl.r1_h0k = pw.w[2 * kPhiloxRounds + 1]; pl.r2_c3k = pw.w[2 * kPhiloxRounds + 2];
+    const uint32_t id_lo = pw.w[2 * kPhiloxRounds + 3];
+    const uint64_t *const in = p.in;
+    const uint8_t *const action = p.action;
+    uint64_t *const out = p.out;
+    int32_t *const reward = p.reward;
+    uint8_t *const done = p.done;
+    const uint64_t g_in = pw.u64(2 * kPhiloxRounds + 4), g_action = pw.u64(2 * kPhiloxRounds + 6),
+                   g_out = pw.u64(2 * kPhiloxRounds + 8), g_reward = pw.u64(2 * kPhiloxRounds + 10),
+                   g_done = pw.u64(2 * kPhiloxRounds + 12);
+    const uint32_t has_reward = pw.w[2 * kPhiloxRounds + 14], has_done = pw.w[2 * kPhiloxRounds + 15];
 
     auto draw = [&](uint32_t board) -> uint32_t {          // the tick's word for board index `board`
-        return philox_launch_word(p.id_lo + board, p.pl, p.keys);
+        return philox_launch_word<WORD>(id_lo + board, pl, keys);
+    };
+    auto first_use = [&] {                                 // before the first lookup of a thread
+        if (REWARD) gate.need_all(); else gate.need_first();
     };
 
-    for (uint32_t u0 = begin + warp * chunk + lane; u0 < end; u0 += trip) {
-        const uint32_t u1 = u0 + 32u;
-        const bool two = dual && u1 < end;
+    // base + index * stride as ONE instruction (IMAD.WIDE); the compiler otherwise spells 64-bit
+    // address arithmetic against a base held in registers as an add-with-carry pair
+    auto at = [](uint64_t base, uint32_t index, uint32_t stride) -> uint64_t {
+        uint64_t a;
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(index), "r"(stride), "l"(base));
+        return a;
+    };
+    // software pipeline: the loads of trip k+1 are issued before trip k is computed, so they have a
+    // whole trip (~3000 cycles) to land (an extra L2 prefetch one trip further ahead measured slower)
+    ulonglong2 nb = make_ulonglong2(0ull, 0ull);
+    uint32_t na16 = 0u;
+    if (VEC && begin + threadIdx.x < end) {
+        nb = ldg_u64x2(at(g_in, begin + threadIdx.x, 16u));
+        na16 = ldg_u16(at(g_action, begin + threadIdx.x, 2u));
+    }
+    for (uint32_t u = begin + threadIdx.x; u < end; u += kThreads) {
         if (VEC) {
-            ulonglong2 b0 = ((const ulonglong2 *)p.in)[u0], b1 = make_ulonglong2(0ull, 0ull);
-            uchar2 a0 = ((const uchar2 *)p.action)[u0], a1 = make_uchar2(0, 0);
-            if (two) { b1 = ((const ulonglong2 *)p.in)[u1]; a1 = ((const uchar2 *)p.action)[u1]; }
-            if (u0 + trip < end) {
-                prefetch_l2((const ulonglong2 *)p.in + u0 + trip);
-                if (dual && u1 + trip < end) prefetch_l2((const ulonglong2 *)p.in + u1 + trip);
-                if ((lane & 15u) == 0u) prefetch_l2((const uchar2 *)p.action + u0 + trip);    // 32 B sectors
-                if (dual && (lane & 15u) == 0u && u1 + trip < end) prefetch_l2((const uchar2 *)p.action + u1 + trip);
+            const ulonglong2 b = nb;
+            const uint32_t a16 = na16;
+            const uchar2 a = make_uchar2((uint8_t)a16, (uint8_t)(a16 >> 8));
+            if (u + kThreads < end) {
+                nb = ldg_u64x2(at(g_in, u + kThreads, 16u));
+                na16 = ldg_u16(at(g_action, u + kThreads, 2u));
             }
-            uint32_t k[4], v[4] = {0u, 0u, 0u, 0u};
+            uint32_t k0, k1, v0 = 0u, v1 = 0u;
             if (INJECT) {
-                const uchar2 kk = ((const uchar2 *)p.spawn_k)[u0], vv = ((const uchar2 *)p.spawn_exp)[u0];
-                k[0] = kk.x; k[1] = kk.y; v[0] = vv.x; v[1] = vv.y; k[2] = k[3] = 0u;
-                if (two) {
-                    const uchar2 kk1 = ((const uchar2 *)p.spawn_k)[u1], vv1 = ((const uchar2 *)p.spawn_exp)[u1];
-                    k[2] = kk1.x; k[3] = kk1.y; v[2] = vv1.x; v[3] = vv1.y;
-                }
+                const uchar2 kk = ((const uchar2 *)p.spawn_k)[u], vv = ((const uchar2 *)p.spawn_exp)[u];
+                k0 = kk.x; k1 = kk.y; v0 = vv.x; v1 = vv.y;
             } else {
-                k[0] = draw(2u * u0); k[1] = draw(2u * u0 + 1u);
-                k[2] = k[3] = 0u;
-                if (two) { k[2] = draw(2u * u1); k[3] = draw(2u * u1 + 1u); }
+                k0 = draw(2u * u); k1 = draw(2u * u + 1u);
             }
-            if (!ready) { mbar_wait(&bar, 0); ready = true; }
-            uint32_t lo[4] = {(uint32_t)b0.x, (uint32_t)b0.y, (uint32_t)b1.x, (uint32_t)b1.y};
-            uint32_t hi[4] = {(uint32_t)(b0.x >> 32), (uint32_t)(b0.y >> 32), (uint32_t)(b1.x >> 32), (uint32_t)(b1.y >> 32)};
-            const uint32_t act[4] = {a0.x, a0.y, a1.x, a1.y};
-            int32_t r[4] = {0, 0, 0, 0};
-            uint32_t d[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int t = 0; t < 2; t++) step_one<REWARD, INJECT>(lo[t], hi[t], act[t], k[t], v[t], smem, lr, p.tables.pc, r[t], d[t], bad);
-            ((ulonglong2 *)p.out)[u0] = make_ulonglong2(((uint64_t)hi[0] << 32) | lo[0], ((uint64_t)hi[1] << 32) | lo[1]);
-            if (p.reward) ((int2 *)p.reward)[u0] = make_int2(r[0], r[1]);
-            if (p.done) ((uchar2 *)p.done)[u0] = make_uchar2((uint8_t)d[0], (uint8_t)d[1]);
-            if (two) {
-#pragma unroll
-                for (int t = 2; t < 4; t++) step_one<REWARD, INJECT>(lo[t], hi[t], act[t], k[t], v[t], smem, lr, p.tables.pc, r[t], d[t], bad);
-                ((ulonglong2 *)p.out)[u1] = make_ulonglong2(((uint64_t)hi[2] << 32) | lo[2], ((uint64_t)hi[3] << 32) | lo[3]);
-                if (p.reward) ((int2 *)p.reward)[u1] = make_int2(r[2], r[3]);
-                if (p.done) ((uchar2 *)p.done)[u1] = make_uchar2((uint8_t)d[2], (uint8_t)d[3]);
+            first_use();
+            uint32_t lo0 = (uint32_t)b.x, hi0 = (uint32_t)(b.x >> 32), lo1 = (uint32_t)b.y, hi1 = (uint32_t)(b.y >> 32);
+            int32_t r0, r1;
+            const bool full0 = step_one<REWARD, INJECT>(lo0, hi0, a.x, k0, v0, smem, lr, p.tables.pc, gate, r0);
+            const bool full1 = step_one<REWARD, INJECT>(lo1, hi1, a.y, k1, v1, smem, lr, p.tables.pc, gate, r1);
+            uint32_t d0 = 0u, d1 = 0u;
+            if (full0 | full1) {                           // rare: Game.has_game_over only where the board is full
+                d0 = (full0 && no_equal_neighbours(lo0, hi0)) ? 1u : 0u;
+                d1 = (full1 && no_equal_neighbours(lo1, hi1)) ? 1u : 0u;
             }
+            if (__builtin_expect((a16 & 0xFCFCu) != 0u, 0)) {            // rare: an action byte > 3
+                bad = 1u;
+                if (a.x > 3u) illegal_action(lo0, hi0, b.x, r0, d0);
+                if (a.y > 3u) illegal_action(lo1, hi1, b.y, r1, d1);
+            }
+            stg_u64x2(at(g_out, u, 16u), ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
+            if (has_reward) stg_u32x2(at(g_reward, u, 8u), (uint32_t)r0, (uint32_t)r1);
+            if (has_done) stg_u16(at(g_done, u, 2u), d0 | (d1 << 8));
         } else {
-            uint64_t b0 = p.in[u0], b1 = 0ull;
-            uint32_t act[2] = {p.action[u0], 0u};
-            if (two) { b1 = p.in[u1]; act[1] = p.action[u1]; }
-            uint32_t k[2], v[2] = {0u, 0u};
-            if (INJECT) {
-                k[0] = p.spawn_k[u0]; v[0] = p.spawn_exp[u0]; k[1] = 0u;
-                if (two) { k[1] = p.spawn_k[u1]; v[1] = p.spawn_exp[u1]; }
-            } else {
-                k[0] = draw(u0); k[1] = two ? draw(u1) : 0u;
-            }
-            if (!ready) { mbar_wait(&bar, 0); ready = true; }
-            uint32_t lo[2] = {(uint32_t)b0, (uint32_t)b1}, hi[2] = {(uint32_t)(b0 >> 32), (uint32_t)(b1 >> 32)};
-            int32_t r[2] = {0, 0};
-            uint32_t d[2] = {0u, 0u};
-            step_one<REWARD, INJECT>(lo[0], hi[0], act[0], k[0], v[0], smem, lr, p.tables.pc, r[0], d[0], bad);
-            p.out[u0] = ((uint64_t)hi[0] << 32) | lo[0];
-            if (p.reward) p.reward[u0] = r[0];
-            if (p.done) p.done[u0] = (uint8_t)d[0];
-            if (two) {
-                step_one<REWARD, INJECT>(lo[1], hi[1], act[1], k[1], v[1], smem, lr, p.tables.pc, r[1], d[1], bad);
-                p.out[u1] = ((uint64_t)hi[1] << 32) | lo[1];
-                if (p.reward) p.reward[u1] = r[1];
-                if (p.done) p.done[u1] = (uint8_t)d[1];
-            }
+            const uint64_t b = in[u];
+            const uint32_t act = action[u];
+            const uint32_t k = INJECT ? (uint32_t)p.spawn_k[u] : draw(u);
+            const uint32_t v = INJECT ? (uint32_t)p.spawn_exp[u] : 0u;
+            first_use();
+            uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d = 0u;
+            int32_t r;
+            const bool full = step_one<REWARD, INJECT>(lo, hi, act, k, v, smem, lr, p.tables.pc, gate, r);
+            if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
+            if (__builtin_expect(act > 3u, 0)) { bad = 1u; illegal_action(lo, hi, b, r, d); }
+            out[u] = ((uint64_t)hi << 32) | lo;
+            if (has_reward) reward[u] = r;
+            if (has_done) done[u] = (uint8_t)d;
         }
     }
     // the odd last board of a vectorised launch
     if (VEC && (p.n & 1u) && blockIdx.x == gridDim.x - 1u && threadIdx.x == 0u) {
         const uint32_t i = p.n - 1u;
-        const uint64_t b0 = p.in[i];
-        uint32_t lo = (uint32_t)b0, hi = (uint32_t)(b0 >> 32), d;
-        int32_t r;
+        const uint64_t b = p.in[i];
+        const uint32_t act = p.action[i];
         const uint32_t k = INJECT ? (uint32_t)p.spawn_k[i] : draw(i);
         const uint32_t v = INJECT ? (uint32_t)p.spawn_exp[i] : 0u;
-        if (!ready) { mbar_wait(&bar, 0); ready = true; }
-        step_one<REWARD, INJECT>(lo, hi, p.action[i], k, v, smem, lr, p.tables.pc, r, d, bad);
+        first_use();
+        uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d = 0u;
+        int32_t r;
+        const bool full = step_one<REWARD, INJECT>(lo, hi, act, k, v, smem, lr, p.tables.pc, gate, r);
+        if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
+        if (act > 3u) { bad = 1u; illegal_action(lo, hi, b, r, d); }
         p.out[i] = ((uint64_t)hi << 32) | lo;
         if (p.reward) p.reward[i] = r;
         if (p.done) p.done[i] = (uint8_t)d;
     }
     if (bad && p.status) atomicOr(p.status, 1);
-    if (!ready) mbar_wait(&bar, 0);          // never leave with the bulk copy in flight
+    gate.need_all();                         // never leave with the bulk copy in flight
 }
 
 // ------------------------------------------------------------------ vectorised env step
@@ -432,11 +501,11 @@ template <bool REWARD>
 __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
-    stage_tables<REWARD>(smem, p.tables, &bar);
+    __shared__ uint64_t bar[2];
+    stage_tables<REWARD>(smem, p.tables, bar);
     const uint32_t lr = smem_u32_pinned(smem);
+    TableGate<REWARD> gate{bar, false, false};
 
-    bool ready = false;
     uint32_t bad = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
@@ -451,13 +520,20 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
             const uint64_t b = p.boards[i];
             const uint32_t a = p.action[i];
             uint32_t st = p.steps[i], ep = p.episodes[i];
+            if (R48_AFTER_PREFETCH && i + stride < p.n) {          // next trip's inputs -> L2 (32-byte sectors)
+                if ((lane & 3u) == 0u) prefetch_l2(p.boards + i + stride);
+                if ((lane & 7u) == 0u) { prefetch_l2(p.steps + i + stride); prefetch_l2(p.episodes + i + stride); }
+                if (lane == 0u) prefetch_l2(p.action + i + stride);
+            }
             uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
             uint32_t aw = draw_word(id, st + 1u, p.keys);
-            if (!ready) { mbar_wait(&bar, 0); ready = true; }
+            if (REWARD) gate.need_all(); else gate.need_first();
             lo = (uint32_t)b; hi = (uint32_t)(b >> 32);
-            uint32_t d;
+            uint32_t d = 0u;
             int32_t r;
-            step_one<REWARD, false>(lo, hi, a, aw, 0u, smem, lr, p.tables.pc, r, d, bad);
+            const bool full = step_one<REWARD, false>(lo, hi, a, aw, 0u, smem, lr, p.tables.pc, gate, r);
+            if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
+            if (a > 3u) { bad = 1u; illegal_action(lo, hi, b, r, d); }
             st += 1u;
             if (p.ring.state && i >= ring_skip) {
                 uint64_t slot = ring_at + (i - ring_skip);
@@ -504,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
         }
     }
     if (bad && p.status) atomicOr(p.status, 1);
-    if (!ready) mbar_wait(&bar, 0);
+    gate.need_all();
     if (p.ring.state) ring_finish(p.ring, p.n);
 }
 
@@ -525,15 +601,18 @@ template <bool REWARD>
 __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
-    stage_tables<REWARD>(smem, p.tables, &bar);
+    __shared__ uint64_t bar[2];
+    stage_tables<REWARD>(smem, p.tables, bar);
     const uint32_t lr = smem_u32_pinned(smem);
+    TableGate<REWARD> gate{bar, false, false};
 
-    bool ready = false;
     const uint32_t stride = gridDim.x * blockDim.x, n = (uint32_t)p.n;     // host splits batches >= 2^30
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t b = p.in[i];
-        if (!ready) { mbar_wait(&bar, 0); ready = true; }
+        // the next trip's boards go to L2 now: this kernel is latency-bound (one 8-byte load in flight
+        // per thread, half occupancy), not bandwidth-bound
+        if (R48_AFTER_PREFETCH && (threadIdx.x & 3u) == 0u && i + stride < n) prefetch_l2(p.in + i + stride);
+        gate.need_all();
         const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
         uint64_t res[4];
         uint32_t rw[4] = {0, 0, 0, 0};
@@ -567,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
         // game over <=> no move changes a non-empty board (proof in DESIGN.md)
         if (p.done) p.done[i] = (uint8_t)(mask == 0u && b != 0ull);
     }
-    if (!ready) mbar_wait(&bar, 0);
+    gate.need_all();
 }
 
 // ------------------------------------------------------------------ fused random rollout
@@ -621,9 +700,9 @@ template <int POLICY, bool RECORD>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[2];
     const uint32_t lr = smem_u32_pinned(smem);
-    stage_tables<false>(smem, p.tables, &bar);
+    stage_tables<false>(smem, p.tables, bar);
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -643,7 +722,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     // tick, every lane in a different sector, made the replay pass LSU-bound (3x the play pass).
     uint32_t tb_lo[4] = {0u, 0u, 0u, 0u}, tb_hi[4] = {0u, 0u, 0u, 0u}, tact = 0u;
     bool live = true;           // the queue may still have work for this lane
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar[0], 0);
+    mbar_wait(&bar[1], 0);
 
     for (;;) {
         const bool fin = live && failed == 3u;          // episode over
@@ -699,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                     axis_word = aw;
                     if (RECORD) { rec_b_lo = lo; rec_b_hi = hi; if ((int32_t)aw >= 0) transpose(rec_b_lo, rec_b_hi); }
                     const uint32_t olo = lo, ohi = hi;
-                    rows_lr<kGuard>(lo, hi, (aw & 0x40000000u) != 0u, lr, p.tables.pc);
+                    rows_lr<kGuard>(lo, hi, pack_selector((aw & 0x40000000u) != 0u), lr, p.tables.pc, [] {});
                     changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
                     // tick 0 is the reset spawn on the empty board (GameClient.py:33-38); an episode
                     // starts at the top of an iteration, so only j == 0 can be it
@@ -771,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                     }
                 }
                 const Blanks b = count_blanks(lo, hi);
-                place_tile_v29(lo, hi, b, __umulhi(aw << 2, b.n), spawn_v29(aw, changed));
+                spawn_tile(lo, hi, b, aw, changed);
                 if (POLICY == kPolicyRandom) {
                     // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
                     const uint32_t axis = 2u - (aw >> 31);
@@ -1141,6 +1221,31 @@ struct DeviceGuard {
     DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+using StepKernel = void (*)(StepParams);
+
+// the instantiation for (reward_mode, injected draws, vector loads, tick & 3)
+template <bool REWARD, bool INJECT, bool VEC>
+StepKernel step_kernel_word(int word)
+{
+    if (INJECT) return step_kernel<REWARD, INJECT, VEC, 0>;
+    switch (word & 3) {
+    case 0: return step_kernel<REWARD, INJECT, VEC, 0>;
+    case 1: return step_kernel<REWARD, INJECT, VEC, 1>;
+    case 2: return step_kernel<REWARD, INJECT, VEC, 2>;
+    default: return step_kernel<REWARD, INJECT, VEC, 3>;
+    }
+}
+
+StepKernel step_kernel_ptr(bool reward, bool inject, bool vec, int word)
+{
+    if (reward) {
+        if (inject) return vec ? step_kernel_word<true, true, true>(word) : step_kernel_word<true, true, false>(word);
+        return vec ? step_kernel_word<true, false, true>(word) : step_kernel_word<true, false, false>(word);
+    }
+    if (inject) return vec ? step_kernel_word<false, true, true>(word) : step_kernel_word<false, true, false>(word);
+    return vec ? step_kernel_word<false, false, true>(word) : step_kernel_word<false, false, false>(word);
+}
+
 template <typename K>
 cudaError_t opt_in_smem(K kernel, uint32_t bytes)
 {
@@ -1157,14 +1262,12 @@ int init_device_locked(int dev, DeviceState &d)
     build_tables_kernel<<<256, 256>>>(d.left, d.merges, d.lr);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    CK(opt_in_smem(step_kernel<false, false, true>, kLrBytes));
-    CK(opt_in_smem(step_kernel<false, false, false>, kLrBytes));
-    CK(opt_in_smem(step_kernel<false, true, true>, kLrBytes));
-    CK(opt_in_smem(step_kernel<false, true, false>, kLrBytes));
-    CK(opt_in_smem(step_kernel<true, false, true>, kLeftBytes + kMergeBytes));
-    CK(opt_in_smem(step_kernel<true, false, false>, kLeftBytes + kMergeBytes));
-    CK(opt_in_smem(step_kernel<true, true, true>, kLeftBytes + kMergeBytes));
-    CK(opt_in_smem(step_kernel<true, true, false>, kLeftBytes + kMergeBytes));
+    for (int reward = 0; reward < 2; reward++)
+        for (int inject = 0; inject < 2; inject++)
+            for (int vec = 0; vec < 2; vec++)
+                for (int word = 0; word < (inject ? 1 : 4); word++)
+                    CK(opt_in_smem(step_kernel_ptr(reward != 0, inject != 0, vec != 0, word),
+                                   reward ? kLeftBytes + kMergeBytes : kLrBytes));
     CK(opt_in_smem(env_step_kernel<false>, kLrBytes));
     CK(opt_in_smem(env_step_kernel<true>, kLeftBytes + kMergeBytes));
     CK(opt_in_smem(afterstates_kernel<false>, kLrBytes));
@@ -1221,6 +1324,8 @@ PhiloxLaunch make_philox_launch(const PhiloxKeys &k, uint32_t id_hi, uint32_t ti
     p.r1_h0k = (uint32_t)(q0 >> 32) ^ k.k1[1];
     p.r2_c3k = (uint32_t)q0 ^ k.k1[2];
     p.word = tick & 3u;
+    p.last_mul = p.word >= 2u ? R48_PHILOX_M0 : R48_PHILOX_M1;
+    p.last_key = p.word >= 2u ? k.k1[kPhiloxRounds - 1] : k.k0[kPhiloxRounds - 1];
     return p;
 }
 
@@ -1294,13 +1399,7 @@ int launch_step(StepParams whole, int64_t whole_n, uint64_t seed, uint64_t board
         const int64_t units = vec ? (m + 1) / 2 : m;
         const int grid = grid_for(units, 32, d.sms, 1);
         const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
-        if (reward_mode) {
-            if (vec) CK(launch_pdl(step_kernel<true, INJECT, true>, grid, kThreads, smem, s, p));
-            else CK(launch_pdl(step_kernel<true, INJECT, false>, grid, kThreads, smem, s, p));
-        } else {
-            if (vec) CK(launch_pdl(step_kernel<false, INJECT, true>, grid, kThreads, smem, s, p));
-            else CK(launch_pdl(step_kernel<false, INJECT, false>, grid, kThreads, smem, s, p));
-        }
+        CK(launch_pdl(step_kernel_ptr(reward_mode != 0, INJECT, vec, (int)(tick & 3u)), grid, kThreads, smem, s, p));
         off += m;
     }
     return R48_OK;

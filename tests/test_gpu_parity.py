@@ -301,7 +301,7 @@ def test_env_step_autoreset_vs_oracle(r48, orc, mode):
     """Policy-in-the-loop stepping: per-env tick/episode counters, auto-reset, fused readout.
     300 steps of a fixed pseudo-random policy take most envs through several episodes."""
     n = 3001
-    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE, reward_mode=mode)
+    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE, reward_mode=mode, id_stride=n)
     boards = orc.reset_batch(n, SEED, BIG_BASE)
     assert (to_u64(env.boards) == boards).all()
     steps = np.zeros(n, np.uint32)
@@ -597,7 +597,7 @@ def test_env_step_in_a_cuda_graph(r48, orc):
     """env_step keeps its counters on the device, so a captured graph replayed k times is k real
     steps (what INTEGRATION.md recommends for launch-bound policy loops)."""
     n, k = 2049, 40
-    env = r48.BatchedGame(n, seed=SEED, board_base=11)
+    env = r48.BatchedGame(n, seed=SEED, board_base=11, id_stride=n)
     a = np.random.default_rng(12).integers(0, 4, n).astype(np.uint8)
     d_a = dev(a)
     side = torch.cuda.Stream()

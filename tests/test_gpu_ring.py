@@ -137,7 +137,7 @@ def test_env_step_appends_its_transitions(r48, orc, mode):
     """the append fused into the env-step kernel: (s, a, r, s', done) of every env, s' being the
     board the step produced (the finished board when done), distinct from s"""
     n, cap = 1500, 4000
-    env = r48.BatchedGame(n, seed=SEED, board_base=77, reward_mode=mode)
+    env = r48.BatchedGame(n, seed=SEED, board_base=77, reward_mode=mode, id_stride=n)
     ring, oring = r48.ReplayRing(cap), orc.Ring(cap)
     boards = orc.reset_batch(n, SEED, 77)
     steps = np.zeros(n, np.uint32)

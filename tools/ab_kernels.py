@@ -20,6 +20,8 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-shared", "-diag-suppress", "186"]
 VARIANTS = {
     "base": [],
+    "nopf": ["-DR48_STEP_PREFETCH=0"],
+    "noapf": ["-DR48_AFTER_PREFETCH=0"],
     "fma": ["-DR48_FMA_INDEX=1"],
     "swz": ["-DR48_SWIZZLE=1"],
     "fmaswz": ["-DR48_FMA_INDEX=1", "-DR48_SWIZZLE=1"],
