@@ -4,9 +4,10 @@
 
 The reference's hot path is Python (game/GameClient.py, control/rand.py, main.py:play), so its
 "build" is byte-compilation: every file is compiled from where it lies under $R48_REFERENCE
-(default /root/reference) into a sourceless .pyc under oracle/_ref/ -- a built artefact like a
-.so (git-ignored, travels to the GPU box with the snapshot); no reference source text enters the
-repository.  The two empty package markers are written here, they are not reference files.
+(default /root/reference) into a marshalled code object under oracle/_ref/ -- a built artefact
+like a .so (git-ignored, travels to the GPU box with the snapshot); no reference source text
+enters the repository.  The files are named *.r48c rather than *.pyc because tree snapshots
+commonly drop *.pyc as interpreter litter; oracle/refarm.py loads them.
 
     python oracle/build_ref.py            # or: make -C oracle _ref
 
@@ -14,8 +15,8 @@ bench.py (`--impl reference`, `cpu_baseline`) imports the result through oracle/
 reports kind "reference"; when oracle/_ref/ is absent it falls back to oracle/pyport.py (kind
 "port") and says so.
 """
+import marshal
 import os
-import py_compile
 import shutil
 import sys
 
@@ -32,12 +33,18 @@ def build(reference=None, quiet=False):
         return None
     if os.path.isdir(DEST):
         shutil.rmtree(DEST)
+    import warnings
     for f in FILES:
-        dst = os.path.join(DEST, f[:-3] + ".pyc")                  # sourceless: next to where the .py would be
+        dst = os.path.join(DEST, f[:-3] + ".r48c")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
-        py_compile.compile(os.path.join(reference, f), cfile=dst, dfile="<reference>/" + f, doraise=True)
-    for pkg in ("game", "control"):
-        open(os.path.join(DEST, pkg, "__init__.py"), "w").close()  # the reference relies on namespace packages
+        with open(os.path.join(reference, f), "rb") as fh:
+            text = fh.read()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", SyntaxWarning)        # main.py's ASCII-art banner has stray backslashes
+            code = compile(text, "<reference>/" + f, "exec", dont_inherit=True)
+        with open(dst, "wb") as fh:
+            fh.write(b"R48C%d.%d\n" % sys.version_info[:2])        # marshal is specific to the minor version
+            marshal.dump(code, fh)
     with open(os.path.join(DEST, "BUILD_INFO"), "w") as fh:
         fh.write("byte-compiled from %s by oracle/build_ref.py with python %s\nfiles: %s\n"
                  % (reference, sys.version.split()[0], " ".join(FILES)))

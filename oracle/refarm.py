@@ -2,31 +2,65 @@
 """The reference's own CPU path, timed: `random.seed(s); Game(); main.play(game, "rand")` over all
 host cores.  TEST / BASELINE INFRASTRUCTURE (same rule as the rest of oracle/).
 
-Runs the unmodified reference from oracle/_ref/ (byte-compiled by oracle/build_ref.py) when that
-directory exists -- kind "reference" -- and oracle/pyport.py otherwise -- kind "port".
+Runs the unmodified reference from oracle/_ref/ (compiled by oracle/build_ref.py) when that
+directory exists and matches this interpreter -- kind "reference" -- and oracle/pyport.py otherwise
+-- kind "port".
 """
+import marshal
 import os
 import random
 import sys
 import time
+import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
+# module name -> compiled file, in import order (main.py:3-8 imports the other three)
+MODULES = (("control.rand", "control/rand.r48c"), ("control.hand", "control/hand.r48c"),
+           ("game.GameClient", "game/GameClient.r48c"), ("r48_reference_main", "main.r48c"))
+_HEADER = b"R48C%d.%d\n" % sys.version_info[:2]
 
 
 def available():
-    return os.path.exists(os.path.join(REF, "game", "GameClient.pyc")) and \
-        os.path.exists(os.path.join(REF, "main.pyc"))
+    try:
+        for _, rel in MODULES:
+            with open(os.path.join(REF, rel), "rb") as fh:
+                if fh.read(len(_HEADER)) != _HEADER:
+                    return False
+        return True
+    except OSError:
+        return False
+
+
+_loaded = None
 
 
 def _load():
-    """(Game, play) of the unmodified reference.  The reference uses top-level packages `game`
-    and `control`, so its build directory goes first on sys.path of the (worker) process."""
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    import importlib
-    main = importlib.import_module("main")             # main.py:3-8 imports game.GameClient, control.*
-    return main.Game, main.play
+    """(Game, play) of the unmodified reference: every compiled module is executed into a module
+    object registered under the name the reference imports it by (`game.GameClient`, `control.rand`,
+    `control.hand`; main.py itself under a private name)."""
+    global _loaded
+    if _loaded:
+        return _loaded
+    for pkg in ("game", "control"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    main = None
+    for name, rel in MODULES:
+        with open(os.path.join(REF, rel), "rb") as fh:
+            fh.read(len(_HEADER))
+            code = marshal.load(fh)
+        mod = types.ModuleType(name)
+        mod.__file__ = os.path.join(REF, rel)
+        sys.modules[name] = mod
+        if "." in name:
+            setattr(sys.modules[name.split(".")[0]], name.split(".")[1], mod)
+        exec(code, mod.__dict__)                       # __name__ != "__main__": main() does not run
+        main = mod
+    _loaded = (main.Game, main.play)
+    return _loaded
 
 
 def play_seeded(seed):

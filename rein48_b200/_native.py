@@ -111,12 +111,15 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        try:
-            build()
-        except (OSError, subprocess.CalledProcessError) as e:
-            raise RuntimeError("libr48.so is missing or was built from other sources, and rebuilding it "
-                               "failed: %s" % e)
-        L = C.CDLL(LIB_PATH)
+        path = os.environ.get("R48_LIBRARY")       # A/B tooling only: a build variant of the same sources
+        if not path:
+            path = LIB_PATH
+            try:
+                build()
+            except (OSError, subprocess.CalledProcessError) as e:
+                raise RuntimeError("libr48.so is missing or was built from other sources, and rebuilding it "
+                                   "failed: %s" % e)
+        L = C.CDLL(path)
         L.r48_version.restype = C.c_int
         if L.r48_version() != VERSION:
             raise RuntimeError("libr48.so reports ABI version %d, this package binds version %d: rebuild it "

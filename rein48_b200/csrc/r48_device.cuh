@@ -83,6 +83,16 @@ __device__ __forceinline__ void stg_u32x2(uint64_t addr, uint32_t x, uint32_t y)
     asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(x), "r"(y));
 }
 
+__device__ __forceinline__ void stg_u64(uint64_t addr, uint64_t v)
+{
+    asm volatile("st.global.u64 [%0], %1;" ::"l"(addr), "l"(v));
+}
+
+__device__ __forceinline__ void stg_u32(uint64_t addr, uint32_t v)
+{
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v));
+}
+
 __device__ __forceinline__ void stg_u16(uint64_t addr, uint32_t v)
 {
     asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"((uint16_t)v));

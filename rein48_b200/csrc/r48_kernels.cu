@@ -701,8 +701,31 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar[2];
+    // the Philox round keys, pinned in registers for the loop (see PinnedWords: whether ptxas keeps
+    // launch constants in uniform registers or re-reads them every iteration changes from build to build)
+    constexpr int kPinned = 2 * kPhiloxRounds + 7;
+    __shared__ uint32_t pin_slots[kPinned];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < kPhiloxRounds; r++) {
+            sts_u32_at(pin_slots + r, p.keys.k0[r]);
+            sts_u32_at(pin_slots + kPhiloxRounds + r, p.keys.k1[r]);
+        }
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 0, (uint64_t)__cvta_generic_to_global(p.final_boards));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 2, (uint64_t)__cvta_generic_to_global(p.lengths));
+        sts_u64_at(pin_slots + 2 * kPhiloxRounds + 4, p.board_base);
+        sts_u32_at(pin_slots + 2 * kPhiloxRounds + 6, p.n);
+    }
     const uint32_t lr = smem_u32_pinned(smem);
-    stage_tables<false>(smem, p.tables, bar);
+    stage_tables<false>(smem, p.tables, bar);             // (its CTA barrier publishes pin_slots)
+    PhiloxKeys keys;
+    PinnedWords<kPinned> pw;
+    pw.fetch(pin_slots);
+#pragma unroll
+    for (int r = 0; r < kPhiloxRounds; r++) { keys.k0[r] = pw.w[r]; keys.k1[r] = pw.w[kPhiloxRounds + r]; }
+    const uint64_t g_final = pw.u64(2 * kPhiloxRounds + 0), g_lengths = pw.u64(2 * kPhiloxRounds + 2);
+    const uint64_t board_base = pw.u64(2 * kPhiloxRounds + 4);
+    const uint32_t n_episodes = pw.w[2 * kPhiloxRounds + 6];
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lanes_below = (1u << lane) - 1u;
@@ -730,8 +753,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         if (__any_sync(kFull, fin)) {
             if (!RECORD && fin && ep != kNone) {
                 if ((int32_t)axis_word >= 0) transpose(lo, hi);
-                p.final_boards[ep] = ((uint64_t)hi << 32) | lo;
-                p.lengths[ep] = last_change;
+                stg_u64(g_final + 8ull * ep, ((uint64_t)hi << 32) | lo);
+                stg_u32(g_lengths + 4ull * ep, last_change);
             }
             const uint32_t want = __ballot_sync(kFull, fin);
             const uint32_t cnt = __popc(want), rem = blk_end - blk_next;
@@ -743,11 +766,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
             if (fin) {
                 const uint32_t rank = __popc(want & lanes_below);
                 const uint32_t mine = rank < rem ? blk_next + rank : fresh + (rank - rem);
-                if (mine < p.n) {
+                if (mine < n_episodes) {
                     ep = mine; lo = 0; hi = 0; tick = 0; failed = 0; axis_word = 0x80000000u;
-                    const uint64_t id = p.board_base + mine;
+                    const uint64_t id = board_base + mine;
                     id_hi = (uint32_t)(id >> 32);
-                    pe = philox_episode((uint32_t)id, p.keys);
+                    pe = philox_episode((uint32_t)id, keys);
                     if (RECORD) { rec_len = p.lengths[mine]; rec_off = p.traj_offsets[mine]; }
                 } else {                       // queue empty: park on the empty board (failed stays 3)
                     live = false; ep = kNone; rec_len = 0;
@@ -760,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         }
 
         uint32_t w[4];
-        philox4x32_episode(id_hi, tick >> 2, pe, p.keys, w);
+        philox4x32_episode(id_hi, tick >> 2, pe, keys, w);
 
         // The tiles of a board sum to at most 4 per spawn, so before tick 4000 no tile can be
         // 16384 and every row is inside the LR table: the range test of rows_lr is provably

@@ -371,3 +371,16 @@ def test_ring_sample_indices_are_uniform(orc):
     first = np.array([ring.sample_indices(1, seed=78, draw_id=d)[0] for d in range(20000)])
     cnt = np.bincount(first, minlength=cap)
     assert chi2.sf(((cnt - 20000 / cap) ** 2 / (20000 / cap)).sum(), cap - 1) > 1e-3
+
+
+def test_compiled_reference_replays_its_own_fingerprints(golden):
+    """oracle/_ref (the unmodified reference, compiled by oracle/build_ref.py; what bench.py's CPU arm
+    runs) plays the seeded episodes recorded in tests/golden from the reference checkout."""
+    from oracle import build_ref, refarm
+    if not refarm.available() and build_ref.build(quiet=True) is None:
+        pytest.skip("no reference checkout and no prebuilt oracle/_ref")
+    fp = golden("episodes_ref.npz")["fingerprint"]
+    for s in range(5):
+        score, steps, mx = refarm.play_seeded(s)
+        assert (steps, score, mx) == tuple(int(x) for x in fp[s])
+    assert refarm.timed_rollouts(16, 2)[2] == "reference"

@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""Turn the scratch captures under gpurun_out/ (tools/collect_profiles.sh) into the committed
+summaries under profiles/ (round 2).  Runs here: reading an .ncu-rep needs no GPU.
+
+    python tools/make_profiles.py
+"""
+import collections
+import csv
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GO = os.path.join(ROOT, "gpurun_out")
+LIB = os.path.join(ROOT, "rein48_b200", "libr48.so")
+PY = sys.executable
+
+
+def run(args, **kw):
+    return subprocess.run(args, capture_output=True, text=True, cwd=ROOT, **kw).stdout
+
+
+def quick_rows(path):
+    rows = list(csv.reader(open(path)))
+    for i, r in enumerate(rows):
+        if r and r[0] == "ID":
+            hdr, start = r, i + 1
+            break
+    idx = {h: i for i, h in enumerate(hdr)}
+    data = collections.OrderedDict()
+    for r in rows[start:]:
+        if len(r) < len(hdr):
+            continue
+        key = (int(r[idx["ID"]]), r[idx["Kernel Name"]])
+        data.setdefault(key, {})[r[idx["Metric Name"]]] = float(r[idx["Metric Value"]].replace(",", ""))
+    return data
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # 1. one JSON summary per full capture
+    names = {"rollout": "rollout", "greedy": "greedy", "traj": "traj", "step1m": "step_1M", "step8m": "step_8M",
+             "after": "afterstates", "env": "env", "ringappend": "ring_append", "ringsample": "ring_sample",
+             "envring": "env_ring"}
+    for tag, name in names.items():
+        rep = os.path.join(GO, "prof_%s.ncu-rep" % tag)
+        if os.path.exists(rep):
+            run([PY, "tools/ncu_summary.py", rep, "--json", os.path.join(OUT, "r02_%s_ncu.json" % name)])
+            print("r02_%s_ncu.json" % name)
+    # bench.py reads r02_step_ncu.json (the 2^20-board launches)
+    src = os.path.join(OUT, "r02_step_1M_ncu.json")
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(OUT, "r02_step_ncu.json"))
+
+    # 2. rollout instructions per env-step at three launch sizes
+    q = os.path.join(GO, "ncuq_r02.csv")
+    log = os.path.join(GO, "ncuq_r02.log")
+    if os.path.exists(q) and os.path.exists(log):
+        steps = {int(m.group(1)): int(m.group(2)) for m in re.finditer(r"rollout 2\^(\d+) env_steps (\d+)", open(log).read())}
+        rolls = [(k, v) for k, v in quick_rows(q).items() if "rollout_kernel" in k[1]]
+        by_size, order = {}, sorted(steps)
+        for i, lg in enumerate(order):                        # two launches per size, in order; take the second
+            v = rolls[2 * i + 1][1]
+            by_size["2^%d" % lg] = {
+                "warp_instructions": v["smsp__inst_executed.sum"], "env_steps": steps[lg],
+                "warp_instr_per_32_steps": v["smsp__inst_executed.sum"] * 32 / steps[lg],
+                "ms": v["gpu__time_duration.sum"] / 1e6, "ipc_per_sm": v["sm__inst_executed.avg.per_cycle_elapsed"],
+                "issue_active_pct": v["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+                "alu_pipe_pct": v["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
+                "fma_pipe_pct": v["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"],
+                "lanes_per_instruction": v["smsp__thread_inst_executed_per_inst_executed.ratio"],
+                "shared_wavefronts": v["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"],
+                "shared_bank_conflict_wavefronts": v["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"],
+                "dram_bytes": v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]}
+        big = by_size["2^%d" % order[-1]]
+        json.dump({
+            "kernel": "r48::rollout_kernel<0,0>", "warp_instr_per_32_steps": big["warp_instr_per_32_steps"],
+            "ipc_per_sm": big["ipc_per_sm"], "issue_active_pct": big["issue_active_pct"], "alu_pipe_pct": big["alu_pipe_pct"],
+            "dram_bytes_per_launch": big["dram_bytes"], "by_launch_size": by_size,
+            "source": "ncu --metrics smsp__inst_executed.sum (tools/ncu_quick.sh) on launches of 2^22, 2^24 and 2^26 episodes; "
+                      "env-steps = sum of the lengths the same launch wrote; the figure used is the 2^26 launch, the bench's size",
+            "issue_note": "ceiling evidence in DESIGN.md 4.4: tools/ubench/pipes.cu tops out at 2.8 warp-instr/cycle/SM for any "
+                          "LOP3/IMAD/PRMT mix, and moving ALU work to the FMA pipe makes the kernel slower "
+                          "(profiles/r02_rollout_fma_variant.txt)",
+            "traffic_note": "dram bytes of the profiled 2^26-episode launch: its 805 MB of per-episode outputs, written once",
+        }, open(os.path.join(OUT, "rollout_issue.json"), "w"), indent=1)
+        print("rollout_issue.json", {k: round(v["warp_instr_per_32_steps"], 2) for k, v in by_size.items()})
+
+    # 3. the rejected FMA-pipe variant next to the default build (same script, same launches)
+    f = os.path.join(GO, "ncuq_fma.csv")
+    if os.path.exists(f) and os.path.exists(q):
+        with open(os.path.join(OUT, "r02_rollout_fma_variant.txt"), "w") as fh:
+            fh.write("rollout_kernel<0,0>, default build vs -DR48_FMA_INDEX=1 (table addresses by IMAD.WIDE / IMAD.HI on the FMA\n"
+                     "pipe instead of SHF + LOP3 on the ALU pipe; multipliers passed as kernel parameters).  ncu --metrics, launches\n"
+                     "of 2^22, 2^24, 2^26 episodes (second launch of each size).  Time does not follow the ALU pipe down: the\n"
+                     "kernel is bound by instruction issue, not by a pipe.\n\n")
+            for label, path in (("default", q), ("fma_index", f)):
+                rolls = [(k, v) for k, v in quick_rows(path).items() if "rollout_kernel" in k[1]]
+                for i in range(1, len(rolls), 2):
+                    v = rolls[i][1]
+                    fh.write("%-10s launch %d: %9.1f us  warp-inst %.4e  IPC %.2f  issue-active %4.1f%%  ALU %4.1f%%  FMA %4.1f%%\n" % (
+                        label, i, v["gpu__time_duration.sum"] / 1e3, v["smsp__inst_executed.sum"],
+                        v["sm__inst_executed.avg.per_cycle_elapsed"], v["smsp__issue_active.avg.pct_of_peak_sustained_active"],
+                        v["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
+                        v["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]))
+        print("r02_rollout_fma_variant.txt")
+
+    # 4. executed-instruction budgets per source function
+    for tag, kern, units, out in (("step8m", "step_kernelILb0ELb0ELb1ELi0", 1 << 23, "r02_step_budget.txt"),):
+        rep = os.path.join(GO, "prof_%s.ncu-rep" % tag)
+        if os.path.exists(rep):
+            txt = run([PY, "tools/sass_budget.py", rep, LIB, kern, str(units), "--lines"])
+            open(os.path.join(OUT, out), "w").write(
+                "Executed warp-instructions per board of r48::step_kernel<0,0,1,0> (2^23 boards at tick 64, config 2's boards),\n"
+                "by source function: tools/sass_budget.py joins ncu's per-instruction execution counts with nvdisasm line info.\n"
+                "'lanes' = average active lanes of those instructions (the transposes run with the vertical half of a warp).\n\n" + txt)
+            print(out)
+    rep = os.path.join(GO, "prof_rollout.ncu-rep")
+    if os.path.exists(rep) and os.path.exists(log):
+        steps = {int(m.group(1)): int(m.group(2)) for m in re.finditer(r"rollout 2\^(\d+) env_steps (\d+)", open(log).read())}
+        # the full capture is the second 2^24 launch of `profile_kernels.py rollout --rollout-log2 24` (seed 2049)
+        m = re.search(r"'steps': (\d+)", open(os.path.join(GO, "prof_rollout.log")).read())
+        units = int(m.group(1)) if m else steps.get(24, 1)
+        txt = run([PY, "tools/sass_budget.py", rep, LIB, "rollout_kernelILi0ELb0", str(units)])
+        open(os.path.join(OUT, "r02_rollout_budget.txt"), "w").write(
+            "Executed warp-instructions per env-step of r48::rollout_kernel<0,0> (2^24 episodes), by source function.\n"
+            "'rollout_kernel' = the loop itself: episode switch, lazy game-over bookkeeping, tick counters.\n\n" + txt)
+        print("r02_rollout_budget.txt")
+
+    # 5. SASS instruction mix of the hot kernels + the markers VERDICT r1 asked for
+    kernels = ["rollout_kernelILi0ELb0", "rollout_kernelILi1ELb0", "rollout_kernelILi0ELb1", "step_kernelILb0ELb0ELb1ELi0",
+               "env_step_kernelILb0", "afterstates_kernelILb0", "ring_append_kernel", "ring_sample_kernel"]
+    sass = run(["cuobjdump", "-sass", LIB])
+    with open(os.path.join(OUT, "r02_sass_mix.txt"), "w") as fh:
+        fh.write("SASS instruction mix of the hot kernels of rein48_b200/libr48.so (python tools/sass_stats.py), sm_100a.\n"
+                 "Bulk-copy engine + mbarrier + programmatic dependent launch are present in every table kernel\n"
+                 "(UBLKCP, SYNCS, ACQBULK, PREEXIT); no tensor-core / TMEM instruction anywhere, by design (nothing is a\n"
+                 "contraction); no local memory (STL / LDL) in any hot kernel.\n\n")
+        for k in kernels:
+            fh.write(run([PY, "tools/sass_stats.py", LIB, k]))
+        tensor = len(re.findall(r"\b(UTCMMA|UTCHMMA|HMMA|IMMA|QGMMA|UTCBAR|LDTM|STTM|UTCCP)\b", sass))
+        fh.write("\ntensor-core / TMEM instructions in the whole library: %d\n" % tensor)
+        fh.write("UBLKCP %d, SYNCS %d, ACQBULK %d, PREEXIT %d in the whole library\n" % tuple(
+            len(re.findall(r"\b%s\b" % op, sass)) for op in ("UBLKCP", "SYNCS", "ACQBULK", "PREEXIT")))
+        local = collections.Counter()
+        cur = None
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                cur = m.group(1)
+            elif re.search(r"\b(STL|LDL)\b", line) and cur:
+                local[cur] += 1
+        fh.write("kernels with local-memory instructions: %s\n" % (dict(local) or "none"))
+    print("r02_sass_mix.txt")
+
+    # 6. launch list of the bench command and the bench lines
+    for name in ("r02_bench_launches.csv",):
+        if os.path.exists(os.path.join(GO, name)):
+            shutil.copy(os.path.join(GO, name), os.path.join(OUT, name))
+            print(name)
+
+
+if __name__ == "__main__":
+    main()

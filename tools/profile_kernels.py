@@ -23,7 +23,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     if a.which == "quick":
         # 2 rollout launches at 2^22 and 2^24, 4 step launches at 2^20 (rotating windows), 2 at 2^23
-        for lg in (22, 24):
+        for lg in (22, 24, 26):
             buf = r48.RolloutBuffers(1 << lg)
             for i in range(2):
                 r48.random_rollouts(1 << lg, seed=2048 + i, buffers=buf, with_stats=False)
@@ -80,6 +80,21 @@ def main():
             r48.random_rollouts(n, seed=2048 + i, buffers=buf, policy="greedy_blanks")
         torch.cuda.synchronize()
         print("greedy", r48.EpisodeStats(buf.stats).summary())
+    if a.which in ("ring", "all"):
+        m, cap = 1 << 20, 1 << 24
+        ring = r48.ReplayRing(cap, seed=7)
+        src = [torch.randint(0, 1 << 62, (m,), device="cuda", dtype=torch.int64) for _ in range(2)]
+        act = torch.randint(0, 4, (m,), device="cuda", dtype=torch.uint8)
+        rw = torch.zeros(m, dtype=torch.int32, device="cuda")
+        for i in range(17 + a.reps):
+            ring.store(src[i & 1], act, rw, src[1 - (i & 1)], act)
+        for i in range(a.reps):
+            ring.sample(m)
+        env = r48.BatchedGame(m, seed=7)
+        for i in range(a.reps + 40):
+            env.env_step(act, ring=ring)
+        torch.cuda.synchronize()
+        print("ring done")
     if a.which in ("traj", "all"):
         for i in range(a.reps):
             tr = r48.rollout_trajectories(1 << 20, seed=2048 + i)
