@@ -21,6 +21,9 @@
 #ifndef R48_SWIZZLE
 #define R48_SWIZZLE 0
 #endif
+#ifndef R48_SPAWN_PRED
+#define R48_SPAWN_PRED 0
+#endif
 
 namespace r48 {
 
@@ -612,9 +615,14 @@ __device__ __forceinline__ void spawn_tile(uint32_t &lo, uint32_t &hi, const Bla
 {
     uint32_t sl, sh;
     kth_blank(b, __umulhi(a << 2, b.n), sl, sh);
+#if R48_SPAWN_PRED
+    const uint32_t v29 = spawn_v29(a, true);
+    if (changed) { lo += __umulhi(sl, v29); hi += __umulhi(sh, v29); }
+#else
     const uint32_t v29 = spawn_v29(a, changed);
     lo += __umulhi(sl, v29);
     hi += __umulhi(sh, v29);
+#endif
 }
 
 // ------------------------------------------------------------------ game over

@@ -230,17 +230,35 @@ struct StepParams {
 // transposed board, between the two transposes (nothing extra to compute); injected draws index
 // the reference's row-major blank list (GameClient.py:109-114), so there the board is transposed
 // back first.
+// The action byte at bit `SHIFT` of `packed` (two actions travel as one 16-bit load), decoded with
+// tests on the packed word itself instead of extracting the byte first: bit 1 clear = UP/DOWN
+// (for the legal codes 0..3; anything else is undone by illegal_action), bit 0 = toward the high end.
+struct Move {
+    bool vertical, toward_high;
+    uint32_t pk;                    // PRMT selector of the table halves (pack_selector)
+};
+
+template <uint32_t SHIFT>
+__device__ __forceinline__ Move decode_move(uint32_t packed)
+{
+    Move m;
+    m.vertical = (packed & (2u << SHIFT)) == 0u;
+    m.toward_high = (packed & (1u << SHIFT)) != 0u;
+    m.pk = SHIFT == 0u ? 0x5410u + 0x2222u * (packed & 1u) : (m.toward_high ? 0x7632u : 0x5410u);
+    return m;
+}
+
 template <bool REWARD, bool INJECT>
-__device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, uint32_t action, uint32_t aw,
+__device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, const Move mv, uint32_t aw,
                                          uint32_t vw, const uint8_t *smem, uint32_t lr, const PipeConsts &pc,
                                          TableGate<REWARD> &gate, int32_t &reward)
 {
-    const bool vertical = is_vertical(action);
+    const bool vertical = mv.vertical;
     if (vertical) transpose(lo, hi);
     const uint32_t olo = lo, ohi = hi;
     uint32_t rw = 0;
-    if (REWARD) rows_l16<true>(lo, hi, is_toward_high(action), (const uint16_t *)smem, smem + kLeftBytes, rw);
-    else rows_lr(lo, hi, pack_selector_of_action(action), lr, pc, [&] { gate.need_second(); });
+    if (REWARD) rows_l16<true>(lo, hi, mv.toward_high, (const uint16_t *)smem, smem + kLeftBytes, rw);
+    else rows_lr(lo, hi, mv.pk, lr, pc, [&] { gate.need_second(); });
     const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
     bool full;
     if (INJECT) {
@@ -371,7 +389,6 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         if (VEC) {
             const ulonglong2 b = nb;
             const uint32_t a16 = na16;
-            const uchar2 a = make_uchar2((uint8_t)a16, (uint8_t)(a16 >> 8));
             if (u + kThreads < end) {
                 nb = ldg_u64x2(at(g_in, u + kThreads, 16u));
                 na16 = ldg_u16(at(g_action, u + kThreads, 2u));
@@ -386,17 +403,24 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             first_use();
             uint32_t lo0 = (uint32_t)b.x, hi0 = (uint32_t)(b.x >> 32), lo1 = (uint32_t)b.y, hi1 = (uint32_t)(b.y >> 32);
             int32_t r0, r1;
-            const bool full0 = step_one<REWARD, INJECT>(lo0, hi0, a.x, k0, v0, smem, lr, p.tables.pc, gate, r0);
-            const bool full1 = step_one<REWARD, INJECT>(lo1, hi1, a.y, k1, v1, smem, lr, p.tables.pc, gate, r1);
+            const bool full0 = step_one<REWARD, INJECT>(lo0, hi0, decode_move<0>(a16), k0, v0, smem, lr, p.tables.pc, gate, r0);
+            const bool full1 = step_one<REWARD, INJECT>(lo1, hi1, decode_move<8>(a16), k1, v1, smem, lr, p.tables.pc, gate, r1);
+            // Game.has_game_over only where the board is full.  On mid-game boards ~3.5 % are, i.e. most
+            // warps have one in some lane and the test's ~25 instructions issue on most trips:
             uint32_t d0 = 0u, d1 = 0u;
-            if (full0 | full1) {                           // rare: Game.has_game_over only where the board is full
-                d0 = (full0 && no_equal_neighbours(lo0, hi0)) ? 1u : 0u;
-                d1 = (full1 && no_equal_neighbours(lo1, hi1)) ? 1u : 0u;
+            if (full0 | full1) {
+                // one pass tests, in every lane that has a full board, ITS full board (the first of the
+                // pair if that one is full, else the second); a lane with both full takes a second pass
+                // (1 lane in 800).  The test costs the same issue slots with 1 or 32 lanes active.
+                const uint32_t tl = full0 ? lo0 : lo1, th = full0 ? hi0 : hi1;
+                const uint32_t dead = no_equal_neighbours(tl, th) ? 1u : 0u;
+                if (full0) d0 = dead; else d1 = dead;
+                if (full0 & full1) d1 = no_equal_neighbours(lo1, hi1) ? 1u : 0u;
             }
             if (__builtin_expect((a16 & 0xFCFCu) != 0u, 0)) {            // rare: an action byte > 3
                 bad = 1u;
-                if (a.x > 3u) illegal_action(lo0, hi0, b.x, r0, d0);
-                if (a.y > 3u) illegal_action(lo1, hi1, b.y, r1, d1);
+                if ((a16 & 0x00FCu) != 0u) illegal_action(lo0, hi0, b.x, r0, d0);
+                if ((a16 & 0xFC00u) != 0u) illegal_action(lo1, hi1, b.y, r1, d1);
             }
             stg_u64x2(at(g_out, u, 16u), ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
             if (has_reward) stg_u32x2(at(g_reward, u, 8u), (uint32_t)r0, (uint32_t)r1);
@@ -409,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             first_use();
             uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d = 0u;
             int32_t r;
-            const bool full = step_one<REWARD, INJECT>(lo, hi, act, k, v, smem, lr, p.tables.pc, gate, r);
+            const bool full = step_one<REWARD, INJECT>(lo, hi, decode_move<0>(act), k, v, smem, lr, p.tables.pc, gate, r);
             if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
             if (__builtin_expect(act > 3u, 0)) { bad = 1u; illegal_action(lo, hi, b, r, d); }
             out[u] = ((uint64_t)hi << 32) | lo;
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         first_use();
         uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32), d = 0u;
         int32_t r;
-        const bool full = step_one<REWARD, INJECT>(lo, hi, act, k, v, smem, lr, p.tables.pc, gate, r);
+        const bool full = step_one<REWARD, INJECT>(lo, hi, decode_move<0>(act), k, v, smem, lr, p.tables.pc, gate, r);
         if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
         if (act > 3u) { bad = 1u; illegal_action(lo, hi, b, r, d); }
         p.out[i] = ((uint64_t)hi << 32) | lo;
@@ -531,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
             lo = (uint32_t)b; hi = (uint32_t)(b >> 32);
             uint32_t d = 0u;
             int32_t r;
-            const bool full = step_one<REWARD, false>(lo, hi, a, aw, 0u, smem, lr, p.tables.pc, gate, r);
+            const bool full = step_one<REWARD, false>(lo, hi, decode_move<0>(a), aw, 0u, smem, lr, p.tables.pc, gate, r);
             if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
             if (a > 3u) { bad = 1u; illegal_action(lo, hi, b, r, d); }
             st += 1u;

@@ -110,12 +110,12 @@ def main():
         print("r02_rollout_fma_variant.txt")
 
     # 4. executed-instruction budgets per source function
-    for tag, kern, units, out in (("step8m", "step_kernelILb0ELb0ELb1ELi0", 1 << 23, "r02_step_budget.txt"),):
+    for tag, kern, units, out in (("step8m", "step_kernelILb0ELb0ELb1ELi1", 1 << 23, "r02_step_budget.txt"),):
         rep = os.path.join(GO, "prof_%s.ncu-rep" % tag)
         if os.path.exists(rep):
             txt = run([PY, "tools/sass_budget.py", rep, LIB, kern, str(units), "--lines"])
             open(os.path.join(OUT, out), "w").write(
-                "Executed warp-instructions per board of r48::step_kernel<0,0,1,0> (2^23 boards at tick 64, config 2's boards),\n"
+                "Executed warp-instructions per board of r48::step_kernel<0,0,1,1> (2^23 boards at tick 65, config 2's boards),\n"
                 "by source function: tools/sass_budget.py joins ncu's per-instruction execution counts with nvdisasm line info.\n"
                 "'lanes' = average active lanes of those instructions (the transposes run with the vertical half of a warp).\n\n" + txt)
             print(out)
