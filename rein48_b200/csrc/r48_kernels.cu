@@ -693,7 +693,8 @@ struct RolloutParams {
 // next episode index (legal because every draw is keyed by the episode's GLOBAL id and tick, not
 // by the lane that plays it), so warps stay full until the queue is empty.  A warp draws indices
 // from a private block of 32 that it refills with one atomic on the global counter: the common
-// switch costs no atomic and no memory round trip.  One Philox call feeds four consecutive ticks.
+// switch costs no atomic and no memory round trip.  One Philox call feeds four consecutive ticks,
+// and a pass of the loop is two calls (eight ticks) between episode-switch checks.
 //
 // Orientation is lazy.  The board is kept transposed after an UP/DOWN move and straight after a
 // LEFT/RIGHT one (the spawn counts blanks in the order of the move's axis, so it runs on the
@@ -704,9 +705,9 @@ struct RolloutParams {
 // Game over is detected lazily: has_game_over (GameClient.py:65-94) holds exactly when no
 // move changes the board, and on a FULL board a horizontal move fails iff no two
 // horizontal neighbours are equal (same for vertical).  So the lane keeps drawing moves and
-// remembers which axes it has seen fail on the current full board; once both have failed
-// the board was dead since the last tick that changed it, and that tick is the episode
-// length.  This replaces a ~20-instruction neighbour test per tick by a few predicated ops
+// remembers which axes it has seen fail since the board last changed; once both have failed and
+// the board is full (tested once per pass, not per tick) the board was dead since the last tick
+// that changed it, and that tick is the episode length.  This replaces a ~20-instruction neighbour test per tick by a few predicated ops
 // at the price of ~3 extra no-op ticks per episode (2 %); outputs are identical.
 enum : int { kPolicyRandom = 0, kPolicyGreedyBlanks = 1 };
 constexpr uint32_t kEpisodeBlock = 32;      // episode indices a warp takes per atomic
@@ -756,7 +757,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     // random policy: `failed` collects the axes seen to fail on the current full board (3 = over);
     // greedy policy: `failed` is simply set to 3 when no move changes the board
-    uint32_t lo = 0, hi = 0, tick = 0, last_change = 0, failed = 3;
+    // (before its first episode a lane holds an all-ones "board": full, with failed == 3, so that the
+    // first pass of the loop sends every lane to the queue)
+    uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu, tick = 0, last_change = 0, failed = 3;
     uint32_t axis_word = 0x80000000u;       // sign bit clear <=> the board is stored transposed
     uint32_t ep = kNone;
     PhiloxEpisode pe = {0u, 0u, 0u};        // per-episode part of the Philox call
@@ -773,7 +776,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
     mbar_wait(&bar[1], 0);
 
     for (;;) {
-        const bool fin = live && failed == 3u;          // episode over
+        // Episode over: both axes have failed since the last change AND the board is full.  The
+        // per-tick bookkeeping records failed axes whether or not the board is full (a failure on a
+        // board with blanks proves nothing, but then the board cannot be full here either: it has not
+        // changed since); testing fullness once per pass is cheaper than once per tick.
+        const bool fin = live && failed == 3u &&
+                         (POLICY != kPolicyRandom || (any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u);
         if (__any_sync(kFull, fin)) {
             if (!RECORD && fin && ep != kNone) {
                 if ((int32_t)axis_word >= 0) transpose(lo, hi);
@@ -806,6 +814,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
             if (!__any_sync(kFull, live)) break;
         }
 
+#ifndef R48_CALLS_PER_ITER
+#define R48_CALLS_PER_ITER 2          // two Philox calls = eight ticks per pass: half as many episode-switch checks
+#endif
+#pragma unroll
+      for (int call = 0; call < R48_CALLS_PER_ITER; call++) {
         uint32_t w[4];
         philox4x32_episode(id_hi, tick >> 2, pe, keys, w);
 
@@ -822,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 bool changed;
                 uint32_t rec_b_lo = 0, rec_b_hi = 0;        // RECORD: the board before the step, straight
                 if (POLICY == kPolicyRandom) {
-                    if ((int32_t)(aw ^ axis_word) < 0) transpose(lo, hi);       // the axis changes
+                    if (((aw ^ axis_word) & 0x80000000u) != 0u) transpose(lo, hi);   // the axis changes
                     axis_word = aw;
                     if (RECORD) { rec_b_lo = lo; rec_b_hi = hi; if ((int32_t)aw >= 0) transpose(rec_b_lo, rec_b_hi); }
                     const uint32_t olo = lo, ohi = hi;
@@ -830,13 +843,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                     changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
                     // tick 0 is the reset spawn on the empty board (GameClient.py:33-38); an episode
                     // starts at the top of an iteration, so only j == 0 can be it
-                    if (j == 0) changed = changed || (tick == 0u);
+                    if (j == 0 && call == 0) changed = changed || (tick == 0u);
                 } else {
                     // All four afterstates: the rows of the stored board give one axis, the rows of
                     // its transpose the other; a candidate stays in the orientation it was computed
                     // in.  key = blanks * 4 + (3 - rotation offset), -1 if the move changes nothing:
                     // the maximum is the greedy choice with the first-best tie rule.
-                    if (j == 0 && tick == 0u) axis_word = aw;                   // the reset draw names its axis
+                    if (j == 0 && call == 0 && tick == 0u) axis_word = aw;      // the reset draw names its axis
                     const bool stored_t = (int32_t)axis_word >= 0;
                     uint32_t yl = lo, yh = hi;
                     transpose(yl, yh);
@@ -872,8 +885,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                         const int key = valid ? (int)(blank_count(cl[c], ch[c]) * 4u + (3u - ((label - rr) & 3u))) : -1;
                         if (key > best) { best = key; bl = cl[c]; bh = ch[c]; taken = label; bflip = c < 2 ? 0u : 1u; }
                     }
-                    changed = best >= 0 || (j == 0 && tick == 0u);
-                    if (best < 0 && !(j == 0 && tick == 0u) && failed != 3u) { failed = 3u; last_change = tick - 1u; }
+                    const bool reset_tick = j == 0 && call == 0 && tick == 0u;
+                    changed = best >= 0 || reset_tick;
+                    if (best < 0 && !reset_tick && failed != 3u) { failed = 3u; last_change = tick - 1u; }
                     lo = bl; hi = bh;
                     if (bflip) axis_word ^= 0x80000000u;
                 }
@@ -902,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 if (POLICY == kPolicyRandom) {
                     // axis bit: 2 for UP/DOWN (aw >> 31 == 0), 1 for LEFT/RIGHT
                     const uint32_t axis = 2u - (aw >> 31);
-                    failed = changed ? 0u : (b.n == 0u ? (failed | axis) : failed);
+                    failed = changed ? 0u : (failed | axis);
                     last_change = changed ? tick : last_change;
                 }
                 tick++;
@@ -911,6 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
         // parked lanes (live == false) sit on the empty board
         if (__all_sync(kFull, tick < 4000u || !live)) four_ticks(std::false_type{});
         else four_ticks(std::true_type{});
+      }
     }
 }
 

@@ -22,7 +22,7 @@ def main():
     torch.cuda.set_device(0)
     n = 3001
     for mode in ("reference", "merge_sum"):
-        env = r48.BatchedGame(n, seed=1, board_base=(1 << 64) - 100, reward_mode=mode)
+        env = r48.BatchedGame(n, seed=1, board_base=(1 << 64) - 100, reward_mode=mode, id_stride=n)
         env.boards.copy_(boards(n, 3, 15))
         for t in range(3):
             env.step(torch.randint(0, 4, (n,), device="cuda"))
@@ -37,6 +37,16 @@ def main():
         r48.random_rollouts(1500, seed=2, policy=pol)
         r48.rollout_trajectories(700, seed=2, policy=pol)
     r48.random_rollouts_host(900, seed=4)
+    r48.random_rollouts_host(900, seed=4, records=True)
+    ring = r48.ReplayRing(1000, seed=3)
+    env = r48.BatchedGame(700, seed=9)
+    for t in range(4):
+        env.env_step(torch.randint(0, 4, (700,), device="cuda"), ring=ring)       # wraps the ring
+    ring.store(b[:333], torch.randint(0, 4, (333,), device="cuda"), None, b[333:666])
+    ring.sample(128); ring.sample(128, replace=True, obs=True); ring.sample(5000)
+    ref = r48.ReplayRing(100, mode="reference")
+    ref.store(b[:333], torch.randint(0, 4, (333,), device="cuda"), None, b[333:666])
+    ref.sample()
     torch.cuda.synchronize()
     print("sanitize pass done")
 
