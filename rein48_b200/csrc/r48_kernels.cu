@@ -536,18 +536,25 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     uint64_t ring_skip = 0, ring_at = 0;
     if (p.ring.state) ring_at = ring_start(p.ring, p.n, ring_skip);
     // warp-uniform trip count: the readout below shuffles boards between the lanes of a warp
+    // software pipeline, as in the step kernel: the inputs of trip k+1 are loaded before trip k is
+    // computed (in place is safe: a trip writes only its own env's slots)
+    uint64_t nb = 0ull;
+    uint32_t na = 0u, nst = 0u, nep = 0u;
+    {
+        const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < p.n) { nb = p.boards[i0]; na = p.action[i0]; nst = p.steps[i0]; nep = p.episodes[i0]; }
+    }
     for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < p.n; base += stride) {
         const uint32_t i = base + lane;
         const bool act = i < p.n;
         uint32_t lo = 0u, hi = 0u;
         if (act) {
-            const uint64_t b = p.boards[i];
-            const uint32_t a = p.action[i];
-            uint32_t st = p.steps[i], ep = p.episodes[i];
-            if (R48_AFTER_PREFETCH && i + stride < p.n) {          // next trip's inputs -> L2 (32-byte sectors)
-                if ((lane & 3u) == 0u) prefetch_l2(p.boards + i + stride);
-                if ((lane & 7u) == 0u) { prefetch_l2(p.steps + i + stride); prefetch_l2(p.episodes + i + stride); }
-                if (lane == 0u) prefetch_l2(p.action + i + stride);
+            const uint64_t b = nb;
+            const uint32_t a = na;
+            uint32_t st = nst, ep = nep;
+            if (i + stride < p.n) {
+                nb = p.boards[i + stride]; na = p.action[i + stride];
+                nst = p.steps[i + stride]; nep = p.episodes[i + stride];
             }
             uint64_t id = p.board_base + i + (uint64_t)ep * p.id_stride;
             uint32_t aw = draw_word(id, st + 1u, p.keys);
@@ -631,11 +638,24 @@ __global__ void __launch_bounds__(kThreads, 1) afterstates_kernel(AfterParams p)
     TableGate<REWARD> gate{bar, false, false};
 
     const uint32_t stride = gridDim.x * blockDim.x, n = (uint32_t)p.n;     // host splits batches >= 2^30
+#ifndef R48_AFTER_PIPE
+#define R48_AFTER_PIPE 1
+#endif
+    // This kernel is latency-bound, not bandwidth-bound (one 8-byte load per thread per trip at half
+    // occupancy): the board of trip k+1 is loaded before trip k is computed, and the one after that
+    // is prefetched into L2.
+    uint64_t next = 0ull;
+    if (R48_AFTER_PIPE && blockIdx.x * blockDim.x + threadIdx.x < n) next = p.in[blockIdx.x * blockDim.x + threadIdx.x];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t b = p.in[i];
-        // the next trip's boards go to L2 now: this kernel is latency-bound (one 8-byte load in flight
-        // per thread, half occupancy), not bandwidth-bound
-        if (R48_AFTER_PREFETCH && (threadIdx.x & 3u) == 0u && i + stride < n) prefetch_l2(p.in + i + stride);
+        uint64_t b;
+        if (R48_AFTER_PIPE) {
+            b = next;
+            if (i + stride < n) next = p.in[i + stride];
+            if (R48_AFTER_PREFETCH && (threadIdx.x & 3u) == 0u && i + 2u * stride < n) prefetch_l2(p.in + i + 2u * stride);
+        } else {
+            b = p.in[i];
+            if (R48_AFTER_PREFETCH && (threadIdx.x & 3u) == 0u && i + stride < n) prefetch_l2(p.in + i + stride);
+        }
         gate.need_all();
         const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
         uint64_t res[4];

@@ -20,7 +20,7 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-shared", "-diag-suppress", "186"]
 VARIANTS = {
     "base": [],
-    "calls2": ["-DR48_CALLS_PER_ITER=2"],
+    "nopipe": ["-DR48_AFTER_PIPE=0"],
     "noapf": ["-DR48_AFTER_PREFETCH=0"],
     "fma": ["-DR48_FMA_INDEX=1"],
     "swz": ["-DR48_SWIZZLE=1"],
