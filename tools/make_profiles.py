@@ -47,7 +47,7 @@ def main():
              "after": "afterstates", "env": "env", "ringappend": "ring_append", "ringsample": "ring_sample",
              "envring": "env_ring"}
     for tag, name in names.items():
-        rep = os.path.join(GO, "prof_%s.ncu-rep" % tag)
+        rep = os.path.join(GO, "prof_%s_raw.csv" % tag)
         if os.path.exists(rep):
             run([PY, "tools/ncu_summary.py", rep, "--json", os.path.join(OUT, "r02_%s_ncu.json" % name)])
             print("r02_%s_ncu.json" % name)
@@ -111,7 +111,7 @@ def main():
 
     # 4. executed-instruction budgets per source function
     for tag, kern, units, out in (("step8m", "step_kernelILb0ELb0ELb1ELi1", 1 << 23, "r02_step_budget.txt"),):
-        rep = os.path.join(GO, "prof_%s.ncu-rep" % tag)
+        rep = os.path.join(GO, "prof_%s_source.csv" % tag)
         if os.path.exists(rep):
             txt = run([PY, "tools/sass_budget.py", rep, LIB, kern, str(units), "--lines"])
             open(os.path.join(OUT, out), "w").write(
@@ -119,7 +119,7 @@ def main():
                 "by source function: tools/sass_budget.py joins ncu's per-instruction execution counts with nvdisasm line info.\n"
                 "'lanes' = average active lanes of those instructions (the transposes run with the vertical half of a warp).\n\n" + txt)
             print(out)
-    rep = os.path.join(GO, "prof_rollout.ncu-rep")
+    rep = os.path.join(GO, "prof_rollout_source.csv")
     if os.path.exists(rep) and os.path.exists(log):
         steps = {int(m.group(1)): int(m.group(2)) for m in re.finditer(r"rollout 2\^(\d+) env_steps (\d+)", open(log).read())}
         # the full capture is the second 2^24 launch of `profile_kernels.py rollout --rollout-log2 24` (seed 2049)

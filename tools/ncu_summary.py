@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read here, no GPU needed) into a small JSON / text record.
 
-    python tools/ncu_summary.py gpurun_out/prof_rollout.ncu-rep [--json out.json]
+    python tools/ncu_summary.py gpurun_out/prof_rollout.ncu-rep|prof_rollout_raw.csv [--json out.json]
 """
 import csv
 import io
@@ -28,7 +28,10 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):                 # an `ncu --page raw --csv` export made on the GPU box
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []

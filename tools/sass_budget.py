@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-component instruction budget of a kernel: EXECUTED warp-instructions per source function.
 
-    python tools/sass_budget.py <report.ncu-rep> <libr48.so> <kernel substring> <units> [--lines]
+    python tools/sass_budget.py <report.ncu-rep | source.csv> <libr48.so> <kernel substring> <units> [--lines]
 
 Joins two views of the same binary:
   * `ncu -i report --page source --csv`  per SASS instruction: "Instructions Executed" (from a
@@ -104,7 +104,10 @@ def disasm(so, kernel):
 
 
 def executed(report, kernel):
-    text = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    if report.endswith(".csv"):              # an `ncu --page source --csv` export made on the GPU box
+        text = open(report).read()
+    else:
+        text = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows, take, hdr = [], False, None
     for r in csv.reader(io.StringIO(text)):
         if r and r[0] == "Kernel Name":
