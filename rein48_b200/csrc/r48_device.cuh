@@ -21,9 +21,7 @@
 #ifndef R48_SWIZZLE
 #define R48_SWIZZLE 0
 #endif
-#ifndef R48_SPAWN_PRED
-#define R48_SPAWN_PRED 0
-#endif
+
 
 namespace r48 {
 
@@ -448,12 +446,6 @@ __device__ __noinline__ uint32_t slow_row(uint32_t r, bool toward_high)
 }
 
 // `lr` below is the shared-window byte address of the staged table (smem_u32)
-__device__ __forceinline__ uint32_t lr_lookup(uint32_t lr, uint32_t r, bool toward_high)
-{
-    if (r < kLrRows) return lds_u32(lr + 4u * lr_slot(r));
-    const uint32_t o = slow_row(r, toward_high);
-    return o | (o << 16);
-}
 
 // The table is staged in two parts: rows below kLrSplit (last cell below 256 -- nearly every row of
 // nearly every board) complete on one barrier, the rest on a second one, so that a launch starts
@@ -468,8 +460,6 @@ constexpr uint32_t kLrSplit = 0x8000u;
 // `pk` = the PRMT selector that re-packs two looked-up rows into a word: 0x5410 takes the low
 // halves (LEFT results), 0x7632 the high halves (RIGHT results).
 __device__ __forceinline__ uint32_t pack_selector(bool toward_high) { return toward_high ? 0x7632u : 0x5410u; }
-// the same from an action code 0..3 (bit 0 = toward high) as one multiply-add
-__device__ __forceinline__ uint32_t pack_selector_of_action(uint32_t action) { return 0x5410u + 0x2222u * (action & 1u); }
 
 template <bool GUARD = true, typename NeedHigh>
 __device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk, uint32_t lr,
@@ -615,14 +605,9 @@ __device__ __forceinline__ void spawn_tile(uint32_t &lo, uint32_t &hi, const Bla
 {
     uint32_t sl, sh;
     kth_blank(b, __umulhi(a << 2, b.n), sl, sh);
-#if R48_SPAWN_PRED
-    const uint32_t v29 = spawn_v29(a, true);
-    if (changed) { lo += __umulhi(sl, v29); hi += __umulhi(sh, v29); }
-#else
     const uint32_t v29 = spawn_v29(a, changed);
     lo += __umulhi(sl, v29);
     hi += __umulhi(sh, v29);
-#endif
 }
 
 // ------------------------------------------------------------------ game over

@@ -305,10 +305,6 @@ __device__ __forceinline__ void prefetch_l2_at(uint64_t global_addr)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(global_addr));
 }
 
-#ifndef R48_STEP_PREFETCH
-#define R48_STEP_PREFETCH 1
-#endif
-
 // WORD = tick & 3 (see philox_launch_word); injected-draw kernels ignore it
 template <bool REWARD, bool INJECT, bool VEC, int WORD>
 __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)

@@ -181,3 +181,39 @@ def test_ring_append_in_a_cuda_graph(r48, orc):
     for _ in range(k + 1):
         oring.append(*b)
     assert_same(ring, oring)
+
+
+def test_ring_full_size_properties(r48):
+    """2^20 envs feeding a 2^22-slot ring for 6 steps (1.5 x capacity), then a 2^18 sample: properties
+    that need no oracle.  A transition conserves the tile sum up to the spawned tile (+0, +2 or +4);
+    done marks exactly the boards no move changes; sampled slots are distinct and inside the ring;
+    next_state is a value of its own (a changed board differs from its predecessor)."""
+    n, cap, b = 1 << 20, 1 << 22, 1 << 18
+    env = r48.BatchedGame(n, seed=SEED)
+    ring = r48.ReplayRing(cap, seed=SEED)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(60):                                                   # mid-game boards first
+        env.env_step(torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g))
+    for _ in range(6):
+        env.env_step(torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g), ring=ring)
+    assert ring.cur_size == cap and int(ring.cursor[0].item()) == 6 * n
+    s = ring.sample(b)
+    idx = s["index"]
+    assert idx.numel() == b and int(idx.min()) >= 0 and int(idx.max()) < cap
+    assert torch.unique(idx).numel() == b                                  # without replacement
+    sc0, _ = r48.scores(s["state"])
+    sc1, _ = r48.scores(s["next_state"])
+    gain = sc1 - sc0
+    changed = s["state"] != s["next_state"]
+    assert bool(((gain == 2) | (gain == 4))[changed].all()) and bool((gain == 0)[~changed].all())
+    _, _, valid, over = r48.afterstates(s["next_state"])
+    assert bool((over == s["done"]).all())
+    assert bool((s["action"] <= 3).all()) and bool((s["reward"] == 0).all())
+    # the move recorded is the move that was made: applying it to `state` gives next_state minus one tile
+    after, _, _, _ = r48.afterstates(s["state"])
+    moved = after.gather(0, s["action"].to(torch.int64)[None, :])[0]
+    diff = moved ^ s["next_state"]
+    nz = torch.zeros_like(diff)
+    for t in range(16):                                                    # number of nibbles that differ
+        nz += ((diff >> (4 * t)) & 15) != 0
+    assert bool((nz[changed] == 1).all()) and bool((nz[~changed] == 0).all())
