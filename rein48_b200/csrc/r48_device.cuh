@@ -60,28 +60,33 @@ __device__ __forceinline__ uint32_t smem_u32_pinned(const void *p)
 // These are volatile asm statements WITHOUT a "memory" clobber on purpose: volatile keeps them in
 // program order among themselves (load, ..., store of one trip), while a clobber would make the
 // compiler re-read every kernel parameter after each of them.
+// OFF: a compile-time byte offset that travels in the instruction's immediate field.
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ ulonglong2 ldg_u64x2(uint64_t addr)
 {
     ulonglong2 v;
-    asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(addr));
+    asm volatile("ld.global.v2.u64 {%0, %1}, [%2+%3];" : "=l"(v.x), "=l"(v.y) : "l"(addr), "n"(OFF));
     return v;
 }
 
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ uint32_t ldg_u16(uint64_t addr)
 {
     uint16_t v;
-    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(addr));
+    asm volatile("ld.global.u16 %0, [%1+%2];" : "=h"(v) : "l"(addr), "n"(OFF));
     return v;
 }
 
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ void stg_u64x2(uint64_t addr, uint64_t x, uint64_t y)
 {
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(addr), "l"(x), "l"(y));
+    asm volatile("st.global.v2.u64 [%0+%3], {%1, %2};" ::"l"(addr), "l"(x), "l"(y), "n"(OFF));
 }
 
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ void stg_u32x2(uint64_t addr, uint32_t x, uint32_t y)
 {
-    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(x), "r"(y));
+    asm volatile("st.global.v2.u32 [%0+%3], {%1, %2};" ::"l"(addr), "r"(x), "r"(y), "n"(OFF));
 }
 
 __device__ __forceinline__ void stg_u64(uint64_t addr, uint64_t v)
@@ -94,9 +99,10 @@ __device__ __forceinline__ void stg_u32(uint64_t addr, uint32_t v)
     asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v));
 }
 
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ void stg_u16(uint64_t addr, uint32_t v)
 {
-    asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"((uint16_t)v));
+    asm volatile("st.global.u16 [%0+%2], %1;" ::"l"(addr), "h"((uint16_t)v), "n"(OFF));
 }
 
 // volatile: must not move above the mbarrier wait that publishes the staged tables

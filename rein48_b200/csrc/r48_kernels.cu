@@ -26,6 +26,18 @@
 
 namespace r48 {
 
+// step_kernel A/B switches (tools/ab_kernels.py).  The two-trip loop body executes
+// 4 % fewer instructions on early-game boards but issues them more slowly (IPC 2.43 against 2.64) and
+// ties at tick 64; the one-trip body is 4 % faster on 2^20 boards, so it is the default.
+#ifndef R48_STEP_UNROLL
+#define R48_STEP_UNROLL 0          // 1: two trips per loop body, immediate-offset addressing
+#endif
+#ifndef R48_STEP_PREFETCH
+#define R48_STEP_PREFETCH 1        // (two-trip body) L2 prefetch distance in loop bodies, 0 = none
+#endif
+#ifndef R48_STEP_GATE_EARLY
+#define R48_STEP_GATE_EARLY 0      // 1: wait for the first half of the table before the loop instead of per trip
+#endif
 #ifndef R48_AFTER_PREFETCH
 #define R48_AFTER_PREFETCH 1
 #endif
@@ -300,9 +312,10 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+template <uint32_t OFF = 0u>
 __device__ __forceinline__ void prefetch_l2_at(uint64_t global_addr)
 {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(global_addr));
+    asm volatile("prefetch.global.L2 [%0+%1];" ::"l"(global_addr), "n"(OFF));
 }
 
 // WORD = tick & 3 (see philox_launch_word); injected-draw kernels ignore it
@@ -373,22 +386,17 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(index), "r"(stride), "l"(base));
         return a;
     };
-    // software pipeline: the loads of trip k+1 are issued before trip k is computed, so they have a
-    // whole trip (~3000 cycles) to land (an extra L2 prefetch one trip further ahead measured slower)
-    ulonglong2 nb = make_ulonglong2(0ull, 0ull);
-    uint32_t na16 = 0u;
-    if (VEC && begin + threadIdx.x < end) {
-        nb = ldg_u64x2(at(g_in, begin + threadIdx.x, 16u));
-        na16 = ldg_u16(at(g_action, begin + threadIdx.x, 2u));
-    }
-    for (uint32_t u = begin + threadIdx.x; u < end; u += kThreads) {
-        if (VEC) {
-            const ulonglong2 b = nb;
-            const uint32_t a16 = na16;
-            if (u + kThreads < end) {
-                nb = ldg_u64x2(at(g_in, u + kThreads, 16u));
-                na16 = ldg_u16(at(g_action, u + kThreads, 2u));
-            }
+    if (VEC) {
+        // One unit (a pair of boards) per thread per trip.  The loop body is TWO trips, A = unit u
+        // and B = unit u + kThreads, each with its own registers for the boards and actions in
+        // flight: the loads of the next A are issued when A's registers die (right after A is
+        // computed), so they have all of B's compute (~3000 cycles) to land, and no register is
+        // ever copied from a "next" to a "current" set.  Every address of the body is one of five
+        // bases plus a compile-time offset that lives in the instruction (R48_STEP_UNROLL=0 builds
+        // the one-trip body with its six moves and ten address instructions per trip for A/B).
+        auto unit = [&](auto off, const ulonglong2 b, const uint32_t a16, const uint32_t u, const uint64_t a_out,
+                        const uint64_t a_reward, const uint64_t a_done) {
+            constexpr uint32_t OFF = decltype(off)::value;          // units past the body's base addresses
             uint32_t k0, k1, v0 = 0u, v1 = 0u;
             if (INJECT) {
                 const uchar2 kk = ((const uchar2 *)p.spawn_k)[u], vv = ((const uchar2 *)p.spawn_exp)[u];
@@ -396,32 +404,89 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             } else {
                 k0 = draw(2u * u); k1 = draw(2u * u + 1u);
             }
-            first_use();
+            if (!R48_STEP_GATE_EARLY) first_use();
             uint32_t lo0 = (uint32_t)b.x, hi0 = (uint32_t)(b.x >> 32), lo1 = (uint32_t)b.y, hi1 = (uint32_t)(b.y >> 32);
             int32_t r0, r1;
             const bool full0 = step_one<REWARD, INJECT>(lo0, hi0, decode_move<0>(a16), k0, v0, smem, lr, p.tables.pc, gate, r0);
             const bool full1 = step_one<REWARD, INJECT>(lo1, hi1, decode_move<8>(a16), k1, v1, smem, lr, p.tables.pc, gate, r1);
             // Game.has_game_over only where the board is full.  On mid-game boards ~3.5 % are, i.e. most
-            // warps have one in some lane and the test's ~25 instructions issue on most trips:
-            uint32_t d0 = 0u, d1 = 0u;
+            // warps have one in some lane and the test's ~25 instructions issue on most trips: one pass
+            // tests, in every lane that has a full board, ITS full board (the first of the pair if that
+            // one is full, else the second); a lane with both full takes a second pass (1 lane in 800).
+            // The test costs the same issue slots with 1 or 32 lanes active.
+            uint32_t dd = 0u;                                        // done bytes of the pair
             if (full0 | full1) {
-                // one pass tests, in every lane that has a full board, ITS full board (the first of the
-                // pair if that one is full, else the second); a lane with both full takes a second pass
-                // (1 lane in 800).  The test costs the same issue slots with 1 or 32 lanes active.
                 const uint32_t tl = full0 ? lo0 : lo1, th = full0 ? hi0 : hi1;
-                const uint32_t dead = no_equal_neighbours(tl, th) ? 1u : 0u;
-                if (full0) d0 = dead; else d1 = dead;
-                if (full0 & full1) d1 = no_equal_neighbours(lo1, hi1) ? 1u : 0u;
+                if (no_equal_neighbours(tl, th)) dd = full0 ? 1u : 0x100u;
+                if ((full0 & full1) && no_equal_neighbours(lo1, hi1)) dd |= 0x100u;
             }
             if (__builtin_expect((a16 & 0xFCFCu) != 0u, 0)) {            // rare: an action byte > 3
                 bad = 1u;
+                uint32_t d0 = dd & 1u, d1 = dd >> 8;
                 if ((a16 & 0x00FCu) != 0u) illegal_action(lo0, hi0, b.x, r0, d0);
                 if ((a16 & 0xFC00u) != 0u) illegal_action(lo1, hi1, b.y, r1, d1);
+                dd = d0 | (d1 << 8);
             }
-            stg_u64x2(at(g_out, u, 16u), ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
-            if (has_reward) stg_u32x2(at(g_reward, u, 8u), (uint32_t)r0, (uint32_t)r1);
-            if (has_done) stg_u16(at(g_done, u, 2u), d0 | (d1 << 8));
-        } else {
+            stg_u64x2<16u * OFF>(a_out, ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
+            if (has_reward) stg_u32x2<8u * OFF>(a_reward, (uint32_t)r0, (uint32_t)r1);
+            if (has_done) stg_u16<2u * OFF>(a_done, dd);
+        };
+        using Off0 = std::integral_constant<uint32_t, 0u>;
+#if R48_STEP_UNROLL
+        using OffT = std::integral_constant<uint32_t, (uint32_t)kThreads>;
+        constexpr uint32_t T = kThreads;
+        uint32_t u = begin + threadIdx.x;
+        // five running addresses (this thread's unit u of each array) instead of five bases + u
+        uint64_t a_in = at(g_in, u, 16u), a_act = at(g_action, u, 2u), a_out = at(g_out, u, 16u),
+                 a_reward = at(g_reward, u, 8u), a_done = at(g_done, u, 2u);
+        ulonglong2 ba = make_ulonglong2(0ull, 0ull), bb = ba;
+        uint32_t aa = 0u, ab = 0u;
+        if (u < end) { ba = ldg_u64x2<0>(a_in); aa = ldg_u16<0>(a_act); }
+        if (u + T < end) { bb = ldg_u64x2<16u * T>(a_in); ab = ldg_u16<2u * T>(a_act); }
+        // the first half of the table is needed from the first lookup on: waiting for it here, with
+        // the first loads in flight, instead of testing a "seen it" flag on every trip
+        if (R48_STEP_GATE_EARLY) first_use();
+        // With the loop this short the kernel is bound by the latency of its own loads (one unit in
+        // flight per thread, ~1 us under load: Little's law gives 3.6 TB/s).  A deeper register
+        // pipeline does not fit in 64 registers, so the units of the body after next are pulled into
+        // L2 by one lane per 128-byte line; the register loads one body ahead then find them there.
+        const uint32_t pf_boards = (threadIdx.x & 7u) == 0u ? end : 0u, pf_actions = (threadIdx.x & 31u) == 0u ? end : 0u;
+        constexpr uint32_t PF = 2u * T * R48_STEP_PREFETCH;           // units ahead of this body's A
+        for (; u < end; u += 2u * T) {
+            if (R48_STEP_PREFETCH) {
+                if (u + PF < pf_boards) prefetch_l2_at<16u * PF>(a_in);
+                if (u + PF + T < pf_boards) prefetch_l2_at<16u * (PF + T)>(a_in);
+                if (u + PF < pf_actions) prefetch_l2_at<2u * PF>(a_act);
+                if (u + PF + T < pf_actions) prefetch_l2_at<2u * (PF + T)>(a_act);
+            }
+            unit(Off0{}, ba, aa, u, a_out, a_reward, a_done);
+            if (u + 2u * T < end) { ba = ldg_u64x2<32u * T>(a_in); aa = ldg_u16<4u * T>(a_act); }
+            if (u + T < end) {
+                unit(OffT{}, bb, ab, u + T, a_out, a_reward, a_done);
+                if (u + 3u * T < end) { bb = ldg_u64x2<48u * T>(a_in); ab = ldg_u16<6u * T>(a_act); }
+            }
+            a_in += 32u * T; a_act += 4u * T; a_out += 32u * T; a_reward += 16u * T; a_done += 4u * T;
+        }
+#else
+        ulonglong2 nb = make_ulonglong2(0ull, 0ull);
+        uint32_t na16 = 0u;
+        if (begin + threadIdx.x < end) {
+            nb = ldg_u64x2<0>(at(g_in, begin + threadIdx.x, 16u));
+            na16 = ldg_u16<0>(at(g_action, begin + threadIdx.x, 2u));
+        }
+        if (R48_STEP_GATE_EARLY) first_use();
+        for (uint32_t u = begin + threadIdx.x; u < end; u += kThreads) {
+            const ulonglong2 b = nb;
+            const uint32_t a16 = na16;
+            if (u + kThreads < end) {
+                nb = ldg_u64x2<0>(at(g_in, u + kThreads, 16u));
+                na16 = ldg_u16<0>(at(g_action, u + kThreads, 2u));
+            }
+            unit(Off0{}, b, a16, u, at(g_out, u, 16u), at(g_reward, u, 8u), at(g_done, u, 2u));
+        }
+#endif
+    } else {
+        for (uint32_t u = begin + threadIdx.x; u < end; u += kThreads) {
             const uint64_t b = in[u];
             const uint32_t act = action[u];
             const uint32_t k = INJECT ? (uint32_t)p.spawn_k[u] : draw(u);

@@ -151,18 +151,52 @@ def test_step_vs_oracle(r48, orc, step, mode):
     env.check_actions()
 
 
-def test_step_bad_action_flag(r48):
-    env = r48.BatchedGame(1000, seed=1)
+@pytest.mark.parametrize("trips", [1, 2, 3, 4, 5])
+def test_step_vs_oracle_multi_trip_slices(r48, orc, trips):
+    """Batches whose per-CTA slice is 1..5 trips of the step kernel's two-trip loop body (1024 pairs of
+    boards per trip and CTA, 148 CTAs), with an odd board count and done boards in every trip."""
+    n = 2 * 148 * (1024 * (trips - 1) + 300) + 1
+    b = random_boards(n, 40 + trips, p_zero=0.08)            # nearly full boards: many end the game
+    a = np.random.default_rng(trips).integers(0, 4, n).astype(np.uint8)
+    env = r48.BatchedGame(n, seed=SEED, board_base=BIG_BASE)
+    env.boards.copy_(boards_to_dev(b))
+    env.steps = 61
+    boards, reward, done = env.step(dev(a))
+    o_b, o_r, o_d = orc.step_batch(b, a, SEED, BIG_BASE, 61)
+    assert (to_u64(boards) == o_b).all()
+    assert (done.cpu().numpy() == o_d).all()
+    assert 0 < int(o_d.sum()) < n
+    assert (reward.cpu().numpy() == o_r).all()
+    env.check_actions()
+
+
+@pytest.mark.parametrize("n", [1000, 2 * 148 * 3400 + 1])          # one trip per CTA / four, odd count
+def test_step_bad_action_flag(r48, orc, n):
+    env = r48.BatchedGame(n, seed=1)
+    for t in range(3):
+        env.step(torch.full((n,), t, dtype=torch.int64, device="cuda"))
     before = env.boards.clone()
-    a = torch.full((1000,), 2, dtype=torch.int64, device="cuda")
-    a[17] = 4
-    a[500] = -1
-    a[501] = 256          # must not wrap into action 0
-    env.step(a)
+    a = torch.full((n,), 2, dtype=torch.int64, device="cuda")
+    bad = {17: 4, 500: -1, 501: 256}            # 256 must not wrap into action 0
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, n, 60 if n > 1000 else 0):
+        bad[int(i)] = int(rng.integers(4, 200))
+    bad[n - 1] = 9
+    for i, v in bad.items():
+        a[i] = v
+    boards, reward, done = env.step(a)
     with pytest.raises(ValueError):
         env.check_actions()
-    for i in (17, 500, 501):
-        assert env.boards[i] == before[i]
+    idx = torch.tensor(sorted(bad), device="cuda")
+    assert (env.boards[idx] == before[idx]).all()
+    assert (reward[idx] == 0).all()
+    # everything else moved LEFT exactly as the oracle says
+    legal = np.full(n, 2, dtype=np.uint8)
+    o_b, o_r, o_d = orc.step_batch(to_u64(before), legal, 1, 0, 3)
+    keep = np.ones(n, dtype=bool)
+    keep[sorted(bad)] = False
+    assert (to_u64(boards)[keep] == o_b[keep]).all()
+    assert (done.cpu().numpy()[keep] == o_d[keep]).all()
 
 
 def test_spawn_vs_oracle(r48, orc):

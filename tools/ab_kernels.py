@@ -20,6 +20,10 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-shared", "-diag-suppress", "186"]
 VARIANTS = {
     "base": [],
+    "unroll": ["-DR48_STEP_UNROLL=1", "-DR48_STEP_GATE_EARLY=1"],          # step_kernel: two trips per loop body
+    "unroll_pf0": ["-DR48_STEP_UNROLL=1", "-DR48_STEP_GATE_EARLY=1", "-DR48_STEP_PREFETCH=0"],
+    "unroll_pf2": ["-DR48_STEP_UNROLL=1", "-DR48_STEP_GATE_EARLY=1", "-DR48_STEP_PREFETCH=2"],
+    "gate_early": ["-DR48_STEP_GATE_EARLY=1"],
     "nopipe": ["-DR48_AFTER_PIPE=0"],
     "noapf": ["-DR48_AFTER_PREFETCH=0"],
     "fma": ["-DR48_FMA_INDEX=1"],
