@@ -463,7 +463,8 @@ def bench_game_adapter(r48):
     dt = time.perf_counter() - t0
     return {"workload": "config 1 through rein48_b200.Game (rng='python'): seeds 0..2, played to game over",
             "env_steps": steps, "env_steps_per_sec": steps / dt, "us_per_step": dt / steps * 1e6,
-            "note": "3 kernel launches + 3 device->host reads per step; the reference's own Python Game.step is "
+            "note": "one launch (r48_step_injected_view: move, spawn, readout and one move of lookahead, through "
+                    "pinned buffers) + one stream synchronize per step; the reference's own Python Game.step is "
                     "~27 us (37 k steps/s per core)"}
 
 

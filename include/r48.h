@@ -134,6 +134,28 @@ int r48_env_step_ring(uint64_t *boards, const uint8_t *action, uint32_t *steps, 
 int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *spawn_exp,
                        int64_t n, void *stream);
 
+/* One move for a player whose policy AND random draws live on the host -- the reference's own
+ * main.play loop (main.py:36-42) over a `Game` (GameClient.py:40-51): Game.step with injected
+ * draws (as r48_step_injected, in place), the readout Game.step returns, and one move of lookahead
+ * so that the host can make the NEXT step's draws in the reference's order without another call.
+ * action[i] = R48_ACTION_NONE skips the move and spawns unconditionally (Game.reset on a zeroed
+ * board, GameClient.py:33-38; spawn_exp[i] = 0 only reads the board out).  An action byte that is
+ * neither 0..3 nor R48_ACTION_NONE leaves the board as it is and sets bit 0 of *status.
+ * All pointers may be device memory or pinned host memory: with pinned buffers a move is one
+ * launch and one cudaStreamSynchronize.  n <= 2^31 - 1 boards, any of which are independent. */
+#define R48_ACTION_NONE 255
+struct r48_game_view {
+    int32_t cells[16];   /* state_matrix: tile VALUES, row-major, 0 = empty */
+    int32_t reward;      /* as r48_step's reward[i] */
+    uint8_t done;        /* Game.has_game_over(new board) */
+    uint8_t valid;       /* bit a: action a (0=UP 1=DOWN 2=LEFT 3=RIGHT) changes the new board */
+    uint8_t blanks[4];   /* blank cells of the new board after action a, before the spawn */
+    uint8_t reserved[2];
+};
+int r48_step_injected_view(uint64_t *boards, const uint8_t *action, const uint8_t *spawn_k,
+                           const uint8_t *spawn_exp, int64_t n, int reward_mode,
+                           struct r48_game_view *views, int32_t *status, void *stream);
+
 /* The same with the draws made on the GPU from the Philox word of (seed, board, tick); there is
  * no move here, so the blanks are counted row-major. */
 int r48_spawn(uint64_t *boards, int64_t n, uint64_t seed, uint64_t board_base, uint32_t tick,

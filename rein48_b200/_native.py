@@ -27,7 +27,7 @@ ROLLOUT_WORKSPACE_BYTES = 256
 # every symbol include/r48.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "r48_version", "r48_build_id", "r48_last_error", "r48_init", "r48_debug_tables_host", "r48_reset", "r48_step",
-    "r48_step_injected", "r48_env_step", "r48_env_step_ring", "r48_spawn_injected", "r48_spawn", "r48_blank_counts",
+    "r48_step_injected", "r48_step_injected_view", "r48_env_step", "r48_env_step_ring", "r48_spawn_injected", "r48_spawn", "r48_blank_counts",
     "r48_afterstates", "r48_rollout", "r48_rollout_policy", "r48_rollout_trajectories", "r48_episode_stats",
     "r48_episode_records", "r48_scores", "r48_decode_f32", "r48_decode_i32", "r48_encode_i32",
     "r48_ring_clear", "r48_ring_append", "r48_ring_sample", "r48_debug_copy22",
@@ -41,6 +41,15 @@ class Ring(C.Structure):
     _fields_ = [("state", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
                 ("next_state", C.c_void_p), ("done", C.c_void_p), ("cursor", C.c_void_p),
                 ("capacity", C.c_uint64)]
+
+
+class GameView(C.Structure):
+    """struct r48_game_view of include/r48.h (r48_step_injected_view writes one per board)."""
+    _fields_ = [("cells", C.c_int32 * 16), ("reward", C.c_int32), ("done", C.c_uint8), ("valid", C.c_uint8),
+                ("blanks", C.c_uint8 * 4), ("reserved", C.c_uint8 * 2)]
+
+
+ACTION_NONE = 255
 
 
 class R48Error(RuntimeError):
@@ -146,6 +155,7 @@ def lib():
         L.r48_debug_copy22.argtypes = [vp, vp, vp, vp, vp, i64, vp]
         L.r48_rollout_host_ex.argtypes = [i64, u64, u64, i32, vp, vp, vp, vp, i32]
         L.r48_spawn_injected.argtypes = [vp, vp, vp, i64, vp]
+        L.r48_step_injected_view.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
         L.r48_spawn.argtypes = [vp, i64, u64, u64, u32, vp]
         L.r48_blank_counts.argtypes = [vp, vp, i64, vp]
         L.r48_afterstates.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]

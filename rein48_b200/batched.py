@@ -307,6 +307,75 @@ def spawn_injected(boards, spawn_k, spawn_exp):
     return boards
 
 
+ACTION_NONE = _native.ACTION_NONE          # r48_step_injected_view: no move, spawn only
+VIEW_DTYPE = None
+
+
+def _view_dtype():
+    """numpy layout of struct r48_game_view (include/r48.h)."""
+    global VIEW_DTYPE
+    if VIEW_DTYPE is None:
+        import numpy as np
+        VIEW_DTYPE = np.dtype([("cells", "<i4", (16,)), ("reward", "<i4"), ("done", "u1"), ("valid", "u1"),
+                               ("blanks", "u1", (4,)), ("reserved", "u1", (2,))])
+        assert VIEW_DTYPE.itemsize == 76
+    return VIEW_DTYPE
+
+
+class HostPlayerViews:
+    """r48_step_injected_view for a player whose policy and random draws live on the host (the
+    reference's main.play over a `Game`): the action, the two injected draws and the result travel
+    through PINNED host buffers the kernel reads and writes directly, so a move is one launch and
+    one stream synchronize -- no copies, no allocation.
+
+        views = HostPlayerViews(boards)          # boards: int64[n] on the GPU, stepped in place
+        v = views.step(actions, spawn_k, spawn_exp)     # numpy record array [n]: cells, reward, done,
+                                                        # valid (bit a: action a changes the new board),
+                                                        # blanks[a] (blank cells after action a)
+    """
+
+    def __init__(self, boards, reward_mode=0):
+        import numpy as np
+        self.boards = _i64(boards)
+        self.device = self.boards.device
+        self.n = self.boards.numel()
+        self.reward_mode = int(reward_mode)
+        self._in = torch.zeros((3, self.n), dtype=torch.uint8).pin_memory()
+        self._out = torch.zeros(self.n * _view_dtype().itemsize, dtype=torch.uint8).pin_memory()
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.inputs = self._in.numpy()                     # [0] action, [1] spawn_k, [2] spawn_exp
+        self.views = self._out.numpy().view(_view_dtype())
+        base = self._in.data_ptr()
+        self._args = (self.boards.data_ptr(), base, base + self.n, base + 2 * self.n, self.n, self.reward_mode,
+                      self._out.data_ptr(), self._status.data_ptr())
+        self._call = _native.lib().r48_step_injected_view
+        self._index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+    def step(self, actions, spawn_k, spawn_exp):
+        """Apply Game.step with injected draws to every board (action 255 = spawn only) and return
+        the views; the returned array is the pinned buffer itself, valid until the next call."""
+        self.inputs[0] = actions
+        self.inputs[1] = spawn_k
+        self.inputs[2] = spawn_exp
+        if torch.cuda.current_device() != self._index:
+            with torch.cuda.device(self.device):
+                return self._launch()
+        return self._launch()
+
+    def _launch(self):
+        stream = torch.cuda.current_stream(self.device)
+        _native.check(self._call(*self._args, stream.cuda_stream))
+        stream.synchronize()
+        return self.views
+
+    def illegal_action_seen(self):
+        """True if any call since the last check carried an action byte other than 0..3 / 255."""
+        bad = bool(self._status.item())
+        if bad:
+            self._status.zero_()
+        return bad
+
+
 def spawn(boards, seed, board_base=0, tick=0):
     """In place: Game.random_fill_grid with the GPU's Philox draws of (seed, board, tick)."""
     boards = _i64(boards)

@@ -214,6 +214,64 @@ __global__ void __launch_bounds__(256) blank_counts_kernel(const uint64_t *__res
     }
 }
 
+// ------------------------------------------------------------------ one call per move for a host-side player
+
+// Game.step with injected draws for a player whose policy AND random draws live on the host (the
+// reference's own main.play loop over the `Game` adapter): one launch does the move, the spawn, the
+// readout (state_matrix as tile values, reward, has_game_over) and looks one move ahead -- for each
+// of the four actions, whether it changes the new board and how many blanks the moved board has,
+// which is exactly what the host needs to make the NEXT step's draws in the reference's order
+// (GameClient.py:121 draws randint(0, n_blank - 1) only if the move changed the board).  Every
+// pointer may be device memory or pinned host memory (the adapter passes pinned buffers, so a
+// move costs one launch and one stream synchronize, no copies).  Uses the 16-bit tables straight
+// from global memory: a handful of boards does not pay for staging 224 KB.
+__global__ void __launch_bounds__(128) game_view_kernel(uint64_t *boards, const uint8_t *action,
+                                                        const uint8_t *spawn_k, const uint8_t *spawn_exp,
+                                                        int64_t n, int reward_mode, r48_game_view *views,
+                                                        int32_t *status, Tables g)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = boards[i];
+    uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    const uint32_t act = action[i];
+    uint32_t rw = 0;
+    bool changed = true;                                   // R48_ACTION_NONE: spawn only (Game.reset)
+    if (act < 4u) {
+        const uint32_t olo = lo, ohi = hi;
+        if (is_vertical(act)) transpose(lo, hi);
+        rows_l16<true>(lo, hi, is_toward_high(act), g.left, g.merges, rw);
+        if (is_vertical(act)) transpose(lo, hi);
+        changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
+    } else if (act != R48_ACTION_NONE) {
+        changed = false;                                   // GameClient.py:254: the caller raises
+        if (status) atomicOr(status, 1);
+    }
+    if (changed) place_tile_checked(lo, hi, count_blanks(lo, hi), spawn_k[i], spawn_exp[i] & 15u);
+    boards[i] = ((uint64_t)hi << 32) | lo;
+    r48_game_view v;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t el = (lo >> (4 * t)) & 15u, eh = (hi >> (4 * t)) & 15u;
+        v.cells[t] = el ? (int32_t)(1u << el) : 0;
+        v.cells[8 + t] = eh ? (int32_t)(1u << eh) : 0;
+    }
+    v.reward = reward_mode != 0 ? (int32_t)rw : 0;
+    v.done = game_over(lo, hi) ? 1 : 0;
+    v.valid = 0;
+#pragma unroll
+    for (uint32_t a = 0; a < 4; a++) {
+        uint32_t l = lo, h = hi, unused;
+        if (is_vertical(a)) transpose(l, h);
+        const uint32_t tl = l, th = h;
+        rows_l16<false>(l, h, is_toward_high(a), g.left, g.merges, unused);
+        if ((l ^ tl) | (h ^ th)) v.valid |= (uint8_t)(1u << a);
+        v.blanks[a] = (uint8_t)count_blanks(l, h).n;       // the same in either orientation
+    }
+    v.reserved[0] = v.reserved[1] = 0;
+    views[i] = v;
+}
+
 // ------------------------------------------------------------------ step
 
 struct StepParams {
@@ -1727,6 +1785,26 @@ int r48_spawn_injected(uint64_t *boards, const uint8_t *spawn_k, const uint8_t *
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     spawn_injected_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(boards, spawn_k, spawn_exp, n);
+    CK(cudaGetLastError());
+    return R48_OK;
+}
+
+int r48_step_injected_view(uint64_t *boards, const uint8_t *action, const uint8_t *spawn_k,
+                           const uint8_t *spawn_exp, int64_t n, int reward_mode,
+                           struct r48_game_view *views, int32_t *status, void *stream)
+{
+    int rc = check_n(n);
+    if (rc) return rc;
+    if (n == 0) return R48_OK;
+    if (!boards || !action || !spawn_k || !spawn_exp || !views)
+        return fail(R48_ERR_NULL, "r48_step_injected_view: NULL pointer");
+    if (!aligned(boards, 8) || !aligned(views, 4))
+        return fail(R48_ERR_ALIGN, "r48_step_injected_view: boards must be 8-byte, views 4-byte aligned");
+    if (reward_mode != 0 && reward_mode != 1) return fail(R48_ERR_ARG, "r48_step_injected_view: reward_mode must be 0 or 1");
+    DeviceState *d;
+    if ((rc = current_device(&d))) return rc;
+    game_view_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        boards, action, spawn_k, spawn_exp, n, reward_mode, views, status, d->tables());
     CK(cudaGetLastError());
     return R48_OK;
 }

@@ -73,24 +73,33 @@ class Game:
         self.rng = rng
         self.device = _device(device)
         self._env = B.BatchedGame(1, seed=seed, device=self.device, board_base=board_id)
+        # one launch + one synchronize per move: action, draws and result go through pinned buffers
+        self._views = B.HostPlayerViews(self._env.boards)
         self.state_matrix = [[0] * 4 for _ in range(4)]
         self.reset()
 
     # ------------------------------------------------------------ public, as in the reference
 
+    def _read_view(self):
+        v = self._views.views[0]
+        self._valid = int(v["valid"])
+        self._blanks = v["blanks"].tolist()
+        return v["cells"].reshape(4, 4).tolist(), int(v["reward"]), bool(v["done"])
+
     def reset(self, display=False):
         env = self._env
         if self.rng == "philox":
             env.reset()
+            self._views.step(B.ACTION_NONE, 0, 0)                        # read the board out
         else:
             env.boards.zero_()
             env.done.zero_()
             env.steps = 0
             k = random.randint(0, 15)                                   # 16 blanks
             vexp = 1 if random.uniform(0, 1) > 0.1 else 2
-            B.spawn_injected(env.boards, [k], [vexp])
+            self._views.step(B.ACTION_NONE, k, vexp)
         # the reference REPLACES the list in reset (GameClient.py:34) and mutates it in step
-        self.state_matrix = _to_matrix(env.boards)
+        self.state_matrix = self._read_view()[0]
         if display:
             Game.print_terminal(self.state_matrix)
         return self.state_matrix
@@ -100,18 +109,20 @@ class Game:
         env = self._env
         if self.rng == "philox":
             env.step([code])
+            self._views.step(B.ACTION_NONE, 0, 0)                        # read the board out
+            new, _, done = self._read_view()
+            reward = int(env.reward.item())
         else:
-            after, _, valid, _ = B.afterstates(env.boards)
             k, vexp = 0, 0
-            if (int(valid.item()) >> code) & 1:                          # has_changed
-                n_blank = int(B.blank_counts(after[code]).item())
-                k = random.randint(0, n_blank - 1)                       # GameClient.py:121
+            if (self._valid >> code) & 1:                                # has_changed
+                k = random.randint(0, self._blanks[code] - 1)            # GameClient.py:121
                 vexp = 1 if random.uniform(0, 1) > 0.1 else 2            # GameClient.py:125
-            env.step_injected([code], [k], [vexp])
-        new = _to_matrix(env.boards)
+            self._views.step(code, k, vexp)
+            env.steps += 1
+            new, reward, done = self._read_view()
         for i in range(4):                       # same list objects, updated in place
             self.state_matrix[i][:] = new[i]
-        return self.state_matrix, int(env.reward.item()), bool(env.done.item())
+        return self.state_matrix, reward, done
 
     # ------------------------------------------------------------ statics, as in the reference
 

@@ -125,6 +125,74 @@ def test_step_injected_vs_oracle_ragged(r48, orc):
         assert (d_d.cpu().numpy()[off:] == o_d).all()
 
 
+def _blank_counts_np(boards):
+    b = np.asarray(boards, dtype=np.uint64)
+    return sum((((b >> np.uint64(4 * t)) & np.uint64(15)) == 0).astype(np.int64) for t in range(16))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_step_injected_view_vs_oracle(r48, orc, mode):
+    """r48_step_injected_view == oracle step with injected draws + decode + has_game_over + the
+    oracle's afterstates of the NEW board (valid mask, blank counts), through pinned host buffers."""
+    rng = np.random.default_rng(21 + mode)
+    n = 5003
+    b = np.concatenate([random_boards(n - 1000, 55), random_boards(1000, 56, p_zero=0.03)])
+    a = rng.integers(0, 4, n).astype(np.uint8)
+    a[::97] = 255                                           # spawn only
+    v = rng.integers(1, 3, n).astype(np.uint8)
+    v[::97 * 3] = 0                                         # ... or just read the board out
+    moved, _, _, _ = orc.afterstates_batch(b)
+    base = np.where(a < 4, moved[np.minimum(a, 3), np.arange(n)], b)
+    blanks = _blank_counts_np(base)
+    k = np.where(blanks > 0, rng.integers(0, 16, n) % np.maximum(blanks, 1), 0).astype(np.uint8)
+    d_b = boards_to_dev(b)
+    views = r48.HostPlayerViews(d_b, reward_mode=mode)
+    got = views.step(a, k, v).copy()
+    assert not views.illegal_action_seen()
+    # expectation: moves through the oracle, spawn-only boards through its random_fill_grid
+    aa = np.where(a < 4, a, 0).astype(np.uint8)
+    o_b, o_r, o_d = orc.step_injected_batch(b, aa, k, v, reward_mode=mode)
+    for i in np.nonzero(a == 255)[0]:
+        m = orc.decode(int(b[i]))
+        if v[i] and blanks[i] > 0:
+            m, _ = orc.random_fill_grid(m, int(k[i]), 1 << int(v[i]))
+        o_b[i], o_r[i], o_d[i] = orc.encode(m), 0, orc.has_game_over(m)
+    assert (to_u64(d_b) == o_b).all()
+    assert (got["cells"].reshape(n, 4, 4) == orc.decode_batch(o_b, dtype="int32")).all()
+    assert (got["reward"] == o_r).all()
+    assert (got["done"] == o_d).all()
+    nxt, _, valid, over = orc.afterstates_batch(o_b)
+    assert (got["valid"] == valid).all()
+    assert (got["done"] == over).all()
+    for act in range(4):
+        assert (got["blanks"][:, act] == _blank_counts_np(nxt[act])).all()
+
+
+def test_step_injected_view_device_buffers_and_bad_action(r48, orc):
+    L = r48._native.lib()
+    n = 300
+    b = random_boards(n, 77)
+    d_b = boards_to_dev(b)
+    a = np.full(n, 2, dtype=np.uint8)
+    a[7] = 4
+    a[200] = 254
+    z = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    views = torch.zeros(n * 76, dtype=torch.uint8, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    one = torch.ones(n, dtype=torch.uint8, device="cuda")
+    r48._native.check(L.r48_step_injected_view(d_b.data_ptr(), dev(a).data_ptr(), z.data_ptr(), one.data_ptr(), n, 0,
+                                               views.data_ptr(), status.data_ptr(), None))
+    assert int(status.item()) == 1
+    out = to_u64(d_b)
+    assert out[7] == b[7] and out[200] == b[200]
+    aa = np.where(a < 4, a, 2).astype(np.uint8)
+    o_b, _, _ = orc.step_injected_batch(b, aa, np.zeros(n, np.uint8), np.ones(n, np.uint8))
+    keep = a < 4
+    assert (out[keep] == o_b[keep]).all()
+    got = views.cpu().numpy().view(r48.batched._view_dtype())
+    assert (got["cells"].reshape(n, 4, 4) == orc.decode_batch(out, dtype="int32")).all()
+
+
 # ------------------------------------------------------------------ step / reset with Philox draws
 
 def test_reset_vs_oracle(r48, orc):
