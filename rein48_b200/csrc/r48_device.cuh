@@ -467,8 +467,24 @@ constexpr uint32_t kLrSplit = 0x8000u;
 // halves (LEFT results), 0x7632 the high halves (RIGHT results).
 __device__ __forceinline__ uint32_t pack_selector(bool toward_high) { return toward_high ? 0x7632u : 0x5410u; }
 
-template <bool GUARD = true, typename NeedHigh>
-__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk, uint32_t lr,
+// where the LR table is read from: the staged copy in shared memory (every shipped kernel), or
+// global memory through the read-only L1 path (the no-staging A/B variant of step_kernel)
+struct TableInShared {
+    uint32_t base;                                   // shared-window byte address (smem_u32)
+    __device__ __forceinline__ uint32_t operator()(uint32_t byte_offset) const { return lds_u32(base + byte_offset); }
+};
+struct TableInGlobal {
+    uint64_t base;                                   // global address of Tables::lr
+    __device__ __forceinline__ uint32_t operator()(uint32_t byte_offset) const
+    {
+        uint32_t v;
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(base + byte_offset));
+        return v;
+    }
+};
+
+template <bool GUARD = true, typename NeedHigh, typename Table>
+__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk, const Table table,
                                         const PipeConsts &pc, NeedHigh need_high)
 {
     const bool toward_high = pk != 0x5410u;          // used on the cold exact path only
@@ -487,8 +503,8 @@ __device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk,
         uint32_t a0, a1, a2, a3;
         row_offsets(lo, pc, a0, a1);
         row_offsets(hi, pc, a2, a3);
-        o0 = lds_u32(lr + a0); o1 = lds_u32(lr + a1);
-        o2 = lds_u32(lr + a2); o3 = lds_u32(lr + a3);
+        o0 = table(a0); o1 = table(a1);
+        o2 = table(a2); o3 = table(a3);
     } else {
         // exact path: one row at a time in a rolled loop, nothing out of line -- a CALL inside the
         // caller's loop would make ptxas reload every launch constant after it, on the hot path too
@@ -498,7 +514,7 @@ __device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk,
         for (uint32_t t = 0; t < 4u; t++) {
             const uint32_t r = (uint32_t)(board >> (16u * t)) & 0xFFFFu;
             uint32_t o;
-            if (r < kLrRows) o = (lds_u32(lr + 4u * lr_slot(r)) >> (toward_high ? 16u : 0u)) & 0xFFFFu;
+            if (r < kLrRows) o = (table(4u * lr_slot(r)) >> (toward_high ? 16u : 0u)) & 0xFFFFu;
             else o = slow_row_inline(r, toward_high);
             moved |= (uint64_t)o << (16u * t);
         }
@@ -507,6 +523,13 @@ __device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk,
     }
     lo = prmt(o0, o1, pk);
     hi = prmt(o2, o3, pk);
+}
+
+template <bool GUARD = true, typename NeedHigh>
+__device__ __forceinline__ void rows_lr(uint32_t &lo, uint32_t &hi, uint32_t pk, uint32_t lr,
+                                        const PipeConsts &pc, NeedHigh need_high)
+{
+    rows_lr<GUARD>(lo, hi, pk, TableInShared{lr}, pc, need_high);
 }
 
 

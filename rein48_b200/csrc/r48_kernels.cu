@@ -38,6 +38,9 @@ namespace r48 {
 #ifndef R48_STEP_GATE_EARLY
 #define R48_STEP_GATE_EARLY 0      // 1: wait for the first half of the table before the loop instead of per trip
 #endif
+#ifndef R48_STEP_TABLE_GLOBAL
+#define R48_STEP_TABLE_GLOBAL 0    // 1: step_kernel (reward_mode 0) reads the LR table from global memory, no staging
+#endif
 #ifndef R48_AFTER_PREFETCH
 #define R48_AFTER_PREFETCH 1
 #endif
@@ -318,9 +321,9 @@ __device__ __forceinline__ Move decode_move(uint32_t packed)
     return m;
 }
 
-template <bool REWARD, bool INJECT>
+template <bool REWARD, bool INJECT, typename Table>
 __device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, const Move mv, uint32_t aw,
-                                         uint32_t vw, const uint8_t *smem, uint32_t lr, const PipeConsts &pc,
+                                         uint32_t vw, const uint8_t *smem, const Table lr, const PipeConsts &pc,
                                          TableGate<REWARD> &gate, int32_t &reward)
 {
     const bool vertical = mv.vertical;
@@ -403,9 +406,20 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         sts_u32_at(pin_slots + 2 * kPhiloxRounds + 14, p.reward != nullptr ? 1u : 0u);
         sts_u32_at(pin_slots + 2 * kPhiloxRounds + 15, p.done != nullptr ? 1u : 0u);
     }
-    stage_tables<REWARD>(smem, p.tables, bar);            // (its CTA barrier publishes pin_slots)
+#if R48_STEP_TABLE_GLOBAL
+    // A/B variant: no staging, the LR table is read where it lies through the read-only L1 path
+    constexpr bool kStaged = REWARD;
+#else
+    constexpr bool kStaged = true;
+#endif
+    if (kStaged) stage_tables<REWARD>(smem, p.tables, bar);            // (its CTA barrier publishes pin_slots)
+    else { __syncthreads(); pdl_launch_dependents(); pdl_wait(); }
+#if R48_STEP_TABLE_GLOBAL
+    const TableInGlobal lr{(uint64_t)__cvta_generic_to_global(p.tables.lr)};
+#else
     const uint32_t lr = smem_u32_pinned(smem);
-    TableGate<REWARD> gate{bar, false, false};
+#endif
+    TableGate<REWARD> gate{bar, !kStaged, !kStaged};
     PinnedWords<kPinned> pw;
     pw.fetch(pin_slots);
 
@@ -452,8 +466,10 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
         // ever copied from a "next" to a "current" set.  Every address of the body is one of five
         // bases plus a compile-time offset that lives in the instruction (R48_STEP_UNROLL=0 builds
         // the one-trip body with its six moves and ten address instructions per trip for A/B).
-        auto unit = [&](auto off, const ulonglong2 b, const uint32_t a16, const uint32_t u, const uint64_t a_out,
-                        const uint64_t a_reward, const uint64_t a_done) {
+        // (a_out/a_reward/a_done: the body's running addresses in the two-trip variant; the one-trip
+        // loop passes zeros and the addresses are made from u where they are used)
+        auto unit = [&](auto off, const ulonglong2 b, const uint32_t a16, const uint32_t u, uint64_t a_out,
+                        uint64_t a_reward, uint64_t a_done) {
             constexpr uint32_t OFF = decltype(off)::value;          // units past the body's base addresses
             uint32_t k0, k1, v0 = 0u, v1 = 0u;
             if (INJECT) {
@@ -472,22 +488,22 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             // tests, in every lane that has a full board, ITS full board (the first of the pair if that
             // one is full, else the second); a lane with both full takes a second pass (1 lane in 800).
             // The test costs the same issue slots with 1 or 32 lanes active.
-            uint32_t dd = 0u;                                        // done bytes of the pair
+            uint32_t d0 = 0u, d1 = 0u;
             if (full0 | full1) {
                 const uint32_t tl = full0 ? lo0 : lo1, th = full0 ? hi0 : hi1;
-                if (no_equal_neighbours(tl, th)) dd = full0 ? 1u : 0x100u;
-                if ((full0 & full1) && no_equal_neighbours(lo1, hi1)) dd |= 0x100u;
+                const uint32_t dead = no_equal_neighbours(tl, th) ? 1u : 0u;
+                if (full0) d0 = dead; else d1 = dead;
+                if (full0 & full1) d1 = no_equal_neighbours(lo1, hi1) ? 1u : 0u;
             }
             if (__builtin_expect((a16 & 0xFCFCu) != 0u, 0)) {            // rare: an action byte > 3
                 bad = 1u;
-                uint32_t d0 = dd & 1u, d1 = dd >> 8;
                 if ((a16 & 0x00FCu) != 0u) illegal_action(lo0, hi0, b.x, r0, d0);
                 if ((a16 & 0xFC00u) != 0u) illegal_action(lo1, hi1, b.y, r1, d1);
-                dd = d0 | (d1 << 8);
             }
+            if (!R48_STEP_UNROLL) { a_out = at(g_out, u, 16u); a_reward = at(g_reward, u, 8u); a_done = at(g_done, u, 2u); }
             stg_u64x2<16u * OFF>(a_out, ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
             if (has_reward) stg_u32x2<8u * OFF>(a_reward, (uint32_t)r0, (uint32_t)r1);
-            if (has_done) stg_u16<2u * OFF>(a_done, dd);
+            if (has_done) stg_u16<2u * OFF>(a_done, d0 | (d1 << 8));
         };
         using Off0 = std::integral_constant<uint32_t, 0u>;
 #if R48_STEP_UNROLL
@@ -540,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
                 nb = ldg_u64x2<0>(at(g_in, u + kThreads, 16u));
                 na16 = ldg_u16<0>(at(g_action, u + kThreads, 2u));
             }
-            unit(Off0{}, b, a16, u, at(g_out, u, 16u), at(g_reward, u, 8u), at(g_done, u, 2u));
+            unit(Off0{}, b, a16, u, 0ull, 0ull, 0ull);
         }
 #endif
     } else {
@@ -1599,7 +1615,7 @@ int launch_step(StepParams whole, int64_t whole_n, uint64_t seed, uint64_t board
         // table staging whether it has work for 1 warp or for 32)
         const int64_t units = vec ? (m + 1) / 2 : m;
         const int grid = grid_for(units, 32, d.sms, 1);
-        const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : kLrBytes;
+        const uint32_t smem = reward_mode ? kLeftBytes + kMergeBytes : (R48_STEP_TABLE_GLOBAL ? 0u : kLrBytes);
         CK(launch_pdl(step_kernel_ptr(reward_mode != 0, INJECT, vec, (int)(tick & 3u)), grid, kThreads, smem, s, p));
         off += m;
     }
