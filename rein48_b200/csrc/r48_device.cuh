@@ -327,6 +327,32 @@ __device__ __forceinline__ void transpose(uint32_t &lo, uint32_t &hi)
     hi = prmt(a, b, 0x7351);
 }
 
+// transpose(lo, hi) in the lanes where `flag` is nonzero, without a branch: the eight block
+// instructions run unconditionally into temporaries and only the two final PRMTs are predicated.
+// Where the condition is per board (the move's axis), some lane of a warp always takes the
+// branch, so a branch never skips anything and its BSSY / BRA / BSYNC are three wasted issue slots
+// per transpose -- in kernels that are bound by issue slots.  (Predicating all ten instructions in
+// PTX does not survive ptxas: it turns predicated writes of temporaries into selects.)
+#ifndef R48_PRED_TRANSPOSE
+#define R48_PRED_TRANSPOSE 1
+#endif
+__device__ __forceinline__ void transpose_where(uint32_t flag, uint32_t &lo, uint32_t &hi)
+{
+#if R48_PRED_TRANSPOSE
+    const uint32_t a = bsel(0x0000F0F0u, lo >> 12, bsel(0xF0F00F0Fu, lo, lo << 12));
+    const uint32_t b = bsel(0x0000F0F0u, hi >> 12, bsel(0xF0F00F0Fu, hi, hi << 12));
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@p prmt.b32 %0, %2, %3, 0x6240;\n\t"
+        "@p prmt.b32 %1, %2, %3, 0x7351;\n\t"
+        "}"
+        : "+r"(lo), "+r"(hi) : "r"(a), "r"(b), "r"(flag));
+#else
+    if (flag) transpose(lo, hi);
+#endif
+}
+
 // swap the two nibbles of every byte (half of a row reversal; the byte swap is folded
 // into the PRMTs that extract / re-pack rows)
 __device__ __forceinline__ uint32_t nibswap(uint32_t w)

@@ -307,7 +307,8 @@ struct StepParams {
 // tests on the packed word itself instead of extracting the byte first: bit 1 clear = UP/DOWN
 // (for the legal codes 0..3; anything else is undone by illegal_action), bit 0 = toward the high end.
 struct Move {
-    bool vertical, toward_high;
+    uint32_t vertical;              // nonzero for UP / DOWN
+    bool toward_high;
     uint32_t pk;                    // PRMT selector of the table halves (pack_selector)
 };
 
@@ -315,7 +316,7 @@ template <uint32_t SHIFT>
 __device__ __forceinline__ Move decode_move(uint32_t packed)
 {
     Move m;
-    m.vertical = (packed & (2u << SHIFT)) == 0u;
+    m.vertical = ~packed & (2u << SHIFT);
     m.toward_high = (packed & (1u << SHIFT)) != 0u;
     m.pk = SHIFT == 0u ? 0x5410u + 0x2222u * (packed & 1u) : (m.toward_high ? 0x7632u : 0x5410u);
     return m;
@@ -326,8 +327,8 @@ __device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, const Move 
                                          uint32_t vw, const uint8_t *smem, const Table lr, const PipeConsts &pc,
                                          TableGate<REWARD> &gate, int32_t &reward)
 {
-    const bool vertical = mv.vertical;
-    if (vertical) transpose(lo, hi);
+    const uint32_t vertical = mv.vertical;
+    transpose_where(vertical, lo, hi);
     const uint32_t olo = lo, ohi = hi;
     uint32_t rw = 0;
     if (REWARD) rows_l16<true>(lo, hi, mv.toward_high, (const uint16_t *)smem, smem + kLeftBytes, rw);
@@ -335,7 +336,7 @@ __device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, const Move 
     const bool changed = ((lo ^ olo) | (hi ^ ohi)) != 0u;
     bool full;
     if (INJECT) {
-        if (vertical) transpose(lo, hi);
+        transpose_where(vertical, lo, hi);
         const Blanks b = count_blanks(lo, hi);
         place_tile_checked(lo, hi, b, aw, changed ? (vw & 15u) : 0u);
         full = (any_zero_nibble(lo) | any_zero_nibble(hi)) == 0u;
@@ -344,7 +345,7 @@ __device__ __forceinline__ bool step_one(uint32_t &lo, uint32_t &hi, const Move 
         spawn_tile(lo, hi, b, aw, changed);
         // full after the spawn <=> the moved board had no blank, or exactly one that was filled
         full = b.n == (changed ? 1u : 0u);
-        if (vertical) transpose(lo, hi);
+        transpose_where(vertical, lo, hi);
     }
     reward = REWARD ? (int32_t)rw : 0;
     return full;
@@ -497,8 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
             }
             if (__builtin_expect((a16 & 0xFCFCu) != 0u, 0)) {            // rare: an action byte > 3
                 bad = 1u;
-                if ((a16 & 0x00FCu) != 0u) illegal_action(lo0, hi0, b.x, r0, d0);
-                if ((a16 & 0xFC00u) != 0u) illegal_action(lo1, hi1, b.y, r1, d1);
+                // (the input pair is read again here rather than kept in four registers for every trip;
+                // nothing has been stored yet, so this is right for in-place calls too)
+                const ulonglong2 again = ldg_u64x2<0>(at(g_in, u, 16u));
+                if ((a16 & 0x00FCu) != 0u) illegal_action(lo0, hi0, again.x, r0, d0);
+                if ((a16 & 0xFC00u) != 0u) illegal_action(lo1, hi1, again.y, r1, d1);
             }
             if (!R48_STEP_UNROLL) { a_out = at(g_out, u, 16u); a_reward = at(g_reward, u, 8u); a_done = at(g_done, u, 2u); }
             stg_u64x2<16u * OFF>(a_out, ((uint64_t)hi0 << 32) | lo0, ((uint64_t)hi1 << 32) | lo1);
@@ -990,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
                 bool changed;
                 uint32_t rec_b_lo = 0, rec_b_hi = 0;        // RECORD: the board before the step, straight
                 if (POLICY == kPolicyRandom) {
-                    if (((aw ^ axis_word) & 0x80000000u) != 0u) transpose(lo, hi);   // the axis changes
+                    transpose_where((aw ^ axis_word) & 0x80000000u, lo, hi);          // the axis changes
                     axis_word = aw;
                     if (RECORD) { rec_b_lo = lo; rec_b_hi = hi; if ((int32_t)aw >= 0) transpose(rec_b_lo, rec_b_hi); }
                     const uint32_t olo = lo, ohi = hi;
