@@ -392,8 +392,8 @@ def bench_env_step_kernel(torch, r48, hbm_peak):
 
 def bench_ring(torch, r48, hbm_peak):
     """the transition ring on its own.  append: 2^20 transitions per call into a ring of
-    2^24 slots (read 22 B + write 22 B per transition); sample: 2^20 distinct slots gathered per call
-    (random 32-byte sectors: the traffic is ~7x the algorithmic bytes by construction)."""
+    2^24 slots (read 22 B, write one 32-byte record per transition); sample: 2^20 distinct slots
+    gathered per call, one random 32-byte record each, written out as separate batch arrays."""
     n, cap = 1 << 20, 1 << 24
     ring = r48.ReplayRing(cap, seed=SEED)
     src = [torch.randint(0, 1 << 62, (n,), device="cuda", dtype=torch.int64) for _ in range(2)]
@@ -415,13 +415,16 @@ def bench_ring(torch, r48, hbm_peak):
                                             bufs["action"].data_ptr(), bufs["reward"].data_ptr(), bufs["next_state"].data_ptr(),
                                             bufs["done"].data_ptr(), None, None, 0, st()))
     ms_s = time_graph(torch, sample, 16)
-    return {"workload": "8(f).4: ring of 2^24 transitions (369 MB), 2^20 per call",
+    return {"workload": "8(f).4: ring of 2^24 transitions (one 32-byte record each, 537 MB), 2^20 per call",
             "append": {"us_per_launch": ms_a * 1e3, "transitions_per_sec": n / (ms_a * 1e-3),
-                       "roofline": hbm_roofline(44 * n, ms_a, hbm_peak, None)},
+                       "roofline": hbm_roofline(44 * n, ms_a, hbm_peak, ncu_traffic("r02_ring_append_ncu.json", 0),
+                                                note="algorithmic: 22 B read + 22 B of payload written per transition; "
+                                                     "the record is padded to one 32-byte sector (54 B moved)")},
             "sample": {"us_per_launch": ms_s * 1e3, "transitions_per_sec": n / (ms_s * 1e-3),
-                       "roofline": hbm_roofline(52 * n, ms_s, hbm_peak, None,
-                                                note="22 B gathered + 30 B written (incl. the int64 slot index) per "
-                                                     "sample; every gathered field costs a 32-byte sector")}}
+                       "roofline": hbm_roofline(52 * n, ms_s, hbm_peak, ncu_traffic("r02_ring_sample_ncu.json", 0),
+                                                note="algorithmic: 22 B of payload gathered + 30 B written (incl. the "
+                                                     "int64 slot index) per sample; a random record is one 32-byte "
+                                                     "sector, which DRAM serves as a 64-byte access")}}
 
 
 def bench_afterstates_kernel(torch, r48, hbm_peak):

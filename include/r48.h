@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define R48_VERSION 200
+#define R48_VERSION 201
 
 #define R48_OK             0
 #define R48_ERR_NULL      -1   /* required pointer is NULL */
@@ -227,17 +227,24 @@ int r48_encode_i32(const int32_t *values, uint64_t *boards, int64_t n, int32_t *
                    void *stream);
 
 /* ---- transition ring: Replay (algorithm/ddpg/replay.py:8-47) for batches, on the device ----
- * Five caller-owned device arrays of `capacity` slots plus a two-word device cursor
+ * One caller-owned device array of `capacity` 32-byte records plus a two-word device cursor
  * (cursor[0] = transitions appended since the last clear, cursor[1] = scratch, both zero
- * initially).  The struct itself lives in HOST memory.  The cursor lives on the device so that
- * appends and samples need no host synchronisation and can be captured in CUDA graphs. */
-typedef struct r48_ring {
-    uint64_t *state;        /* board before the step            (ddpg.py:31 `state`)      */
-    uint8_t  *action;
-    int32_t  *reward;
-    uint64_t *next_state;   /* board after the step, a distinct value (ddpg.py:29-31 stores
+ * initially).  A record is one DRAM sector, so gathering a random slot costs one sector (as five
+ * separate arrays a sample read 19 times the bytes it returned).  The r48_ring struct itself
+ * lives in HOST memory.  The cursor lives on the device so that appends and samples need no host
+ * synchronisation and can be captured in CUDA graphs. */
+typedef struct r48_transition {
+    uint64_t state;         /* board before the step            (ddpg.py:31 `state`)      */
+    uint64_t next_state;    /* board after the step, a distinct value (ddpg.py:29-31 stores
                                the SAME list object twice; that aliasing is not reproduced) */
-    uint8_t  *done;
+    int32_t  reward;
+    uint8_t  action;
+    uint8_t  done;
+    uint8_t  reserved[10];  /* written as zero */
+} r48_transition;           /* 32 bytes */
+
+typedef struct r48_ring {
+    r48_transition *slots;  /* [capacity], 32-byte aligned */
     uint64_t *cursor;       /* [2] */
     uint64_t  capacity;     /* Replay.max_size (replay.py:11) */
 } r48_ring;

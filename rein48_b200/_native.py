@@ -33,14 +33,13 @@ SYMBOLS = (
     "r48_ring_clear", "r48_ring_append", "r48_ring_sample", "r48_debug_copy22",
     "r48_step_host", "r48_afterstates_host", "r48_rollout_host", "r48_rollout_host_ex", "r48_shutdown",
 )
-VERSION = 200
+VERSION = 201
 
 
 class Ring(C.Structure):
-    """struct r48_ring of include/r48.h (a host struct of device pointers)."""
-    _fields_ = [("state", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
-                ("next_state", C.c_void_p), ("done", C.c_void_p), ("cursor", C.c_void_p),
-                ("capacity", C.c_uint64)]
+    """struct r48_ring of include/r48.h (a host struct of device pointers); `slots` points at
+    `capacity` 32-byte r48_transition records."""
+    _fields_ = [("slots", C.c_void_p), ("cursor", C.c_void_p), ("capacity", C.c_uint64)]
 
 
 class GameView(C.Structure):

@@ -603,17 +603,36 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(StepParams p)
 
 // ------------------------------------------------------------------ vectorised env step
 
-// Optional transition ring (SoA; see r48_ring_append): slot (cursor[0] + i) % capacity receives
-// the transition of env i; the last CTA to finish adds n to cursor[0].
+// Optional transition ring (see r48_ring_append): slot (cursor[0] + i) % capacity receives the
+// transition of env i; the last CTA to finish adds n to cursor[0].  A slot is one 32-byte record
+// (r48_transition: one DRAM sector), written and read as two 128-bit words.
 struct RingRefs {
-    uint64_t *state;
-    uint8_t *action;
-    int32_t *reward;
-    uint64_t *next_state;
-    uint8_t *done;
+    r48_transition *slots;
     uint64_t *cursor;            // [0] transitions appended so far, [1] CTA ticket (zero between launches)
     uint64_t capacity;
 };
+
+// (one 256-bit access per record -- LDG/STG.E.ENL2.256, new with sm_100 -- so that every store
+// instruction of a warp writes whole sectors: as two 128-bit halves an append ran at 4.0 TB/s)
+__device__ __forceinline__ void ring_put(const RingRefs &r, uint64_t slot, uint64_t state, uint32_t action,
+                                         int32_t reward, uint64_t next_state, uint32_t done)
+{
+    const uint64_t word2 = (uint64_t)(uint32_t)reward | ((uint64_t)(action & 0xFFu) << 32) | ((uint64_t)(done & 0xFFu) << 40);
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};"
+                 ::"l"(r.slots + slot), "l"(state), "l"(next_state), "l"(word2), "l"(0ull) : "memory");
+}
+
+__device__ __forceinline__ void ring_get(const RingRefs &r, uint64_t slot, uint64_t &state, uint32_t &action,
+                                         int32_t &reward, uint64_t &next_state, uint32_t &done)
+{
+    uint64_t word2, unused;
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(state), "=l"(next_state), "=l"(word2), "=l"(unused) : "l"(r.slots + slot));
+    (void)unused;
+    reward = (int32_t)(uint32_t)word2;
+    action = (uint32_t)(word2 >> 32) & 0xFFu;
+    done = (uint32_t)(word2 >> 40) & 0xFFu;
+}
 
 // first slot of an append of n (<= capacity unless `skip` says otherwise) transitions and the
 // number of leading items that a later item of the same append would overwrite anyway
@@ -654,7 +673,7 @@ struct EnvParams {
     int auto_reset;
     PhiloxKeys keys;
     Tables tables;
-    RingRefs ring;               // ring.state == NULL: no ring
+    RingRefs ring;               // ring.slots == NULL: no ring
 };
 
 // Game.step with per-env tick / episode counters, optional auto-reset, the float readout and the
@@ -673,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t ring_skip = 0, ring_at = 0;
-    if (p.ring.state) ring_at = ring_start(p.ring, p.n, ring_skip);
+    if (p.ring.slots) ring_at = ring_start(p.ring, p.n, ring_skip);
     // warp-uniform trip count: the readout below shuffles boards between the lanes of a warp
     // software pipeline, as in the step kernel: the inputs of trip k+1 are loaded before trip k is
     // computed (in place is safe: a trip writes only its own env's slots)
@@ -705,14 +724,11 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
             if (full) d = no_equal_neighbours(lo, hi) ? 1u : 0u;
             if (a > 3u) { bad = 1u; illegal_action(lo, hi, b, r, d); }
             st += 1u;
-            if (p.ring.state && i >= ring_skip) {
+            if (p.ring.slots && i >= ring_skip) {
                 uint64_t slot = ring_at + (i - ring_skip);
                 if (slot >= p.ring.capacity) slot -= p.ring.capacity;
-                p.ring.state[slot] = b;
-                p.ring.action[slot] = (uint8_t)a;
-                p.ring.reward[slot] = r;
-                p.ring.next_state[slot] = ((uint64_t)hi << 32) | lo;      // the board the step produced,
-                p.ring.done[slot] = (uint8_t)d;                            // not the auto-reset one
+                // next_state = the board the step produced, not the auto-reset one
+                ring_put(p.ring, slot, b, a, r, ((uint64_t)hi << 32) | lo, d);
             }
             if (d && p.auto_reset) {                 // rare: a lane's game ended
                 if (p.final_boards) p.final_boards[i] = ((uint64_t)hi << 32) | lo;
@@ -751,7 +767,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(EnvParams p)
     }
     if (bad && p.status) atomicOr(p.status, 1);
     gate.need_all();
-    if (p.ring.state) ring_finish(p.ring, p.n);
+    if (p.ring.slots) ring_finish(p.ring, p.n);
 }
 
 // ------------------------------------------------------------------ afterstates
@@ -1205,8 +1221,10 @@ __global__ void __launch_bounds__(256) records_kernel(const uint64_t *__restrict
 }
 
 // ------------------------------------------------------------------ transition ring
-// Replay.store / Replay.sample (algorithm/ddpg/replay.py:8-47) for batches of transitions, as five
-// device arrays of `capacity` slots: state, action, reward, next_state, done.
+// Replay.store / Replay.sample (algorithm/ddpg/replay.py:8-47) for batches of transitions, as one
+// device array of `capacity` 32-byte records (state, next_state, reward, action, done): a random
+// slot is one DRAM sector.  (Round 2's first layout, five arrays, made a sample gather five sectors
+// -- 431 MB of DRAM reads for 23 MB of sampled transitions.)
 
 struct RingAppendParams {
     RingRefs ring;
@@ -1234,11 +1252,8 @@ __global__ void __launch_bounds__(256) ring_append_kernel(RingAppendParams p)
          i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t slot = at + (i - skip);
         if (slot >= cap) slot -= cap;
-        p.ring.state[slot] = p.state[i];
-        p.ring.action[slot] = p.action[i];
-        p.ring.reward[slot] = p.reward ? p.reward[i] : 0;
-        p.ring.next_state[slot] = p.next_state[i];
-        p.ring.done[slot] = p.done ? p.done[i] : (uint8_t)0;
+        ring_put(p.ring, slot, p.state[i], p.action[i], p.reward ? p.reward[i] : 0, p.next_state[i],
+                 p.done ? (uint32_t)p.done[i] : 0u);
     }
     ring_finish(p.ring, take);
 }
@@ -1339,12 +1354,15 @@ __global__ void __launch_bounds__(256) ring_sample_kernel(RingSampleParams p)
         }
         if (p.out_index) p.out_index[i] = idx;
         if (idx < 0) continue;
-        const uint64_t s = p.ring.state[idx], nx = p.ring.next_state[idx];
+        uint64_t s, nx;
+        uint32_t act, dn;
+        int32_t rw;
+        ring_get(p.ring, (uint64_t)idx, s, act, rw, nx, dn);
         p.out_state[i] = s;
         p.out_next[i] = nx;
-        p.out_action[i] = p.ring.action[idx];
-        p.out_reward[i] = p.ring.reward[idx];
-        p.out_done[i] = p.ring.done[idx];
+        p.out_action[i] = (uint8_t)act;
+        p.out_reward[i] = rw;
+        p.out_done[i] = (uint8_t)dn;
         if (p.obs_state || p.obs_next) {
 #pragma unroll
             for (int row = 0; row < 4; row++) {
@@ -1649,12 +1667,11 @@ inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int ring_refs(const r48_ring *ring, RingRefs *out, const char *who)
 {
-    if (!ring || !ring->state || !ring->action || !ring->reward || !ring->next_state || !ring->done || !ring->cursor)
-        return fail(R48_ERR_NULL, who);
+    if (!ring || !ring->slots || !ring->cursor) return fail(R48_ERR_NULL, who);
     if (ring->capacity == 0 || ring->capacity > ((uint64_t)1 << 40)) return fail(R48_ERR_ARG, "ring capacity must be in 1 .. 2^40");
-    if (!aligned(ring->state, 8) || !aligned(ring->next_state, 8) || !aligned(ring->reward, 4) || !aligned(ring->cursor, 8))
-        return fail(R48_ERR_ALIGN, "ring arrays are misaligned");
-    *out = RingRefs{ring->state, ring->action, ring->reward, ring->next_state, ring->done, ring->cursor, ring->capacity};
+    if (!aligned(ring->slots, 32) || !aligned(ring->cursor, 8))
+        return fail(R48_ERR_ALIGN, "ring slots must be 32-byte aligned, the cursor 8-byte aligned");
+    *out = RingRefs{ring->slots, ring->cursor, ring->capacity};
     return R48_OK;
 }
 

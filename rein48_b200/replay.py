@@ -5,9 +5,10 @@ transitions, resident on the GPU.
 The reference keeps a Python list of [state, action, reward, next_state] (ddpg.py:31), refuses
 new items once `max_size` are stored (replay.py:18-21), samples `batch_size` of them without
 replacement (random.sample, :33) and empties itself after every sample (:26).  Here the items
-are five device arrays of `capacity` slots (state, action, reward, next_state, done) filled by
-`r48_ring_append` -- or directly by the env-step kernel, `BatchedGame.env_step(ring=...)` -- and
-gathered by `r48_ring_sample`; nothing crosses to the host.
+are `capacity` 32-byte records (state, next_state, reward, action, done: one DRAM sector each, so
+a sampled slot costs one sector) in one device array, filled by `r48_ring_append` -- or directly
+by the env-step kernel, `BatchedGame.env_step(ring=...)` -- and gathered by `r48_ring_sample`
+into separate batch tensors; nothing crosses to the host.
 
   mode="ring"       overwrite the oldest slot when full, sampling does not clear  (the usual
                     DQN replay; what the fused env-step append does)
@@ -41,18 +42,38 @@ class ReplayRing:
         self.appended = 0              # host mirror of the device cursor (no sync needed to know the size)
         c = self.capacity
         with torch.cuda.device(self.device):
-            self.state = torch.zeros(c, dtype=torch.int64, device=self.device)
-            self.action = torch.zeros(c, dtype=torch.uint8, device=self.device)
-            self.reward = torch.zeros(c, dtype=torch.int32, device=self.device)
-            self.next_state = torch.zeros(c, dtype=torch.int64, device=self.device)
-            self.done = torch.zeros(c, dtype=torch.uint8, device=self.device)
+            # [capacity][4] int64 = r48_transition[capacity]: state, next_state, reward|action<<32|done<<40, 0
+            self.slots = torch.zeros((c, 4), dtype=torch.int64, device=self.device)
             self.cursor = torch.zeros(2, dtype=torch.int64, device=self.device)
-        self._struct = _native.Ring(self.state.data_ptr(), self.action.data_ptr(), self.reward.data_ptr(),
-                                    self.next_state.data_ptr(), self.done.data_ptr(), self.cursor.data_ptr(), c)
+        if self.slots.data_ptr() % 32:
+            raise RuntimeError("ring storage is not 32-byte aligned")
+        self._struct = _native.Ring(self.slots.data_ptr(), self.cursor.data_ptr(), c)
         self._lib = _native.lib()
 
     def _ref(self):
         return C.byref(self._struct)
+
+    # the stored fields as tensors of `capacity` elements (views / unpacked copies of the records;
+    # for inspection and tests -- learners take batches from sample())
+    @property
+    def state(self):
+        return self.slots[:, 0].contiguous()
+
+    @property
+    def next_state(self):
+        return self.slots[:, 1].contiguous()
+
+    @property
+    def reward(self):
+        return (self.slots[:, 2] & 0xFFFFFFFF).to(torch.int32)
+
+    @property
+    def action(self):
+        return ((self.slots[:, 2] >> 32) & 0xFF).to(torch.uint8)
+
+    @property
+    def done(self):
+        return ((self.slots[:, 2] >> 40) & 0xFF).to(torch.uint8)
 
     def _appended(self, n):
         if self.mode == "reference":

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(native):
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r"\bT (r48_[a-z0-9_]+)", out)))
     assert exported == declared
-    assert L.r48_version() == 200 == native.VERSION
+    assert L.r48_version() == 201 == native.VERSION
     assert native.built_id() == native.source_id() and L.r48_build_id().decode().endswith(native.source_id())
 
 
@@ -73,12 +73,16 @@ def test_argument_validation_needs_no_device(native):
     assert L.r48_rollout(0, 0, 0, None, None, None, None, None) == native.OK
     assert b"NULL" in L.r48_last_error()
     # transition ring: struct and argument checks
-    ring = native.Ring(p, p, p, p, p, p, 0)
+    big = (ctypes.c_uint64 * 16)()
+    q = (ctypes.addressof(big) + 31) & ~31                                      # a 32-byte aligned record
+    ring = native.Ring(q, p, 0)
     assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 1, 0, None) == native.ERR_ARG     # capacity 0
     ring.capacity = 4
-    ring.reward = None
+    ring.slots = None
     assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 1, 0, None) == native.ERR_NULL
-    ring.reward = p
+    ring.slots = q + 8
+    assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 1, 0, None) == native.ERR_ALIGN
+    ring.slots = q
     assert L.r48_ring_append(ctypes.byref(ring), p, p, None, p, None, 0, 0, None) == native.OK          # empty append
     assert L.r48_ring_append(ctypes.byref(ring), None, p, None, p, None, 2, 0, None) == native.ERR_NULL
     assert L.r48_ring_sample(ctypes.byref(ring), 2, 0, 0, 0, None, None, p, p, p, p, None, None, 0, None) == native.ERR_NULL
