@@ -622,17 +622,18 @@ __device__ __forceinline__ void ring_put(const RingRefs &r, uint64_t slot, uint6
                  ::"l"(r.slots + slot), "l"(state), "l"(next_state), "l"(word2), "l"(0ull) : "memory");
 }
 
+#pragma nv_diag_suppress 550            // the fourth word of the 256-bit load is padding
 __device__ __forceinline__ void ring_get(const RingRefs &r, uint64_t slot, uint64_t &state, uint32_t &action,
                                          int32_t &reward, uint64_t &next_state, uint32_t &done)
 {
     uint64_t word2, unused;
     asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(state), "=l"(next_state), "=l"(word2), "=l"(unused) : "l"(r.slots + slot));
-    (void)unused;
     reward = (int32_t)(uint32_t)word2;
     action = (uint32_t)(word2 >> 32) & 0xFFu;
     done = (uint32_t)(word2 >> 40) & 0xFFu;
 }
+#pragma nv_diag_default 550
 
 // first slot of an append of n (<= capacity unless `skip` says otherwise) transitions and the
 // number of leading items that a later item of the same append would overwrite anyway
