@@ -646,7 +646,7 @@ def run_ours(args):
                          "ipc_per_sm_implied": per_gpu_rate * w / 32 / (148 * sm_mhz * 1e6),
                          "peak_formula": "148 SMs x 4 schedulers x sm_mhz (median under load) x 32 lanes / "
                                          "warp-instructions per 32 env-steps (ncu); frac = issue-slot utilisation",
-                         "issue_note": prof.get("issue_note"),
+                         "issue_note": prof.get("issue_note"), "history": prof.get("history"),
                          "traffic": prof.get("dram_bytes_per_launch"),
                          "traffic_note": prof.get("traffic_note")})
     line = {

@@ -86,6 +86,10 @@ def main():
             "issue_note": "ceiling evidence in DESIGN.md 4.4: tools/ubench/pipes.cu tops out at 2.8 warp-instr/cycle/SM for any "
                           "LOP3/IMAD/PRMT mix, and moving ALU work to the FMA pipe makes the kernel slower "
                           "(profiles/r02_rollout_fma_variant.txt)",
+            "history": "warp-instructions per 32 env-steps: r01 132.4 (IPC 2.77, frac 0.73), r02 88.2 (IPC 2.75): the peak of "
+                       "this roofline is inversely proportional to the instruction count, so cutting instructions raises "
+                       "the value and the peak together; frac is the share of issue slots used, value is what improved "
+                       "(2.02e11 -> 2.86e11 env-steps/s per GPU)",
             "traffic_note": "dram bytes of the profiled 2^26-episode launch: its 805 MB of per-episode outputs, written once",
         }, open(os.path.join(OUT, "rollout_issue.json"), "w"), indent=1)
         print("rollout_issue.json", {k: round(v["warp_instr_per_32_steps"], 2) for k, v in by_size.items()})
