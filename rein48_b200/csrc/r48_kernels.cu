@@ -2268,16 +2268,18 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
     uint64_t *d_stats = (uint64_t *)(d->arena + o_stats);
     cudaStream_t s = d->stream, c = d->copy_stream;
     if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
-    // Large batches go in chunks of 2^23 episodes: the per-episode results of chunk i travel to
-    // the host on the copy stream while chunk i+1 is being played.
+    // Large batches go in chunks of 2^24 episodes: the per-episode results of chunk i travel to
+    // the host on the copy stream while chunk i+1 is being played (67 MB of records per chunk: 1.2 ms
+    // of PCIe under 8 ms of play; every chunk costs ~0.1 ms in launch tails and gaps, so not smaller).
     // The copy of the LAST chunk is the only one left exposed, so the chunks shrink toward the end
-    // (..., 2^23, 2^22, 2^21, 2^20, 2^20): small chunks run a little less efficiently but hide
+    // (..., 2^24, 2^23, 2^22, 2^21, 2^20, 2^20): small chunks run a little less efficiently but hide
     // most of that tail.
-    const int64_t big = (int64_t)1 << 23, small = (int64_t)1 << 20;
+    const int64_t big = (int64_t)1 << 24, small = (int64_t)1 << 20;
     int slot = 0;
     for (int64_t off = 0, m = 0; off < n; off += m, slot ^= 1) {
         const int64_t left = n - off;
-        if (n <= ((int64_t)1 << 24)) m = left;                 // small batches: one launch
+        if (n <= ((int64_t)1 << 23) || !(final_boards || lengths || records))
+            m = left;                                          // small batches, or nothing to copy per episode: one launch
         else if (left > 2 * big) m = big;
         else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
         else m = left;
