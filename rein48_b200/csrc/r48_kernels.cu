@@ -1107,9 +1107,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
 
 // ------------------------------------------------------------------ episode statistics
 
+// (`records`, optional: the packed per-episode word of records_kernel, written in the same pass --
+// the host path wants both and the score is computed here anyway)
 __global__ void __launch_bounds__(256) stats_kernel(const uint64_t *__restrict__ boards,
                                                     const uint32_t *__restrict__ lengths, int64_t n,
-                                                    unsigned long long *stats)
+                                                    unsigned long long *stats, uint32_t *records)
 {
     __shared__ uint32_t h_max[16], h_len[2048], h_score[2048];
     __shared__ unsigned long long sums[5];
@@ -1144,6 +1146,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const uint64_t *__restrict__
         if (++pending == 255u) flush_max();
         atomicAdd(&h_len[min(ln, 2047u)], 1u);
         atomicAdd(&h_score[min(sc >> 1, 2047u)], 1u);
+        if (records) records[i] = ((sc >> 1) << 13) | min(ln, 8191u);
         cnt += 1; s_len += ln; s_sc += sc;
         s_sc2 += (unsigned long long)sc * sc;
         s_len2 += (unsigned long long)ln * ln;
@@ -1933,7 +1936,7 @@ int r48_episode_stats(const uint64_t *final_boards, const uint32_t *lengths, int
     DeviceState *d;
     if ((rc = current_device(&d))) return rc;
     stats_kernel<<<grid_for(n, 256, d->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        final_boards, lengths, n, (unsigned long long *)stats);
+        final_boards, lengths, n, (unsigned long long *)stats, nullptr);
     CK(cudaGetLastError());
     return R48_OK;
 }
@@ -2283,10 +2286,16 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
         else if (left > 2 * big) m = big;
         else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
         else m = left;
-        rc = r48_rollout_policy(m, seed, board_base + (uint64_t)off, policy, d_fb + off, d_len + off,
-                                stats ? d_stats : nullptr, d->arena + o_ws, s);
+        rc = r48_rollout_policy(m, seed, board_base + (uint64_t)off, policy, d_fb + off, d_len + off, nullptr,
+                                d->arena + o_ws, s);
         if (rc) return rc;
-        if (records && (rc = r48_episode_records(d_fb + off, d_len + off, d_rec + off, m, s))) return rc;
+        if (stats) {                                           // statistics and records in one pass over the chunk
+            stats_kernel<<<grid_for(m, 256, d->sms, 8), 256, 0, s>>>(d_fb + off, d_len + off, m,
+                                                                     (unsigned long long *)d_stats, records ? d_rec + off : nullptr);
+            CK(cudaGetLastError());
+        } else if (records && (rc = r48_episode_records(d_fb + off, d_len + off, d_rec + off, m, s))) {
+            return rc;
+        }
         if (final_boards || lengths || records) {
             CK(cudaEventRecord(d->chunk_done[slot], s));
             CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
