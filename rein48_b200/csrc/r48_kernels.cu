@@ -41,6 +41,9 @@ namespace r48 {
 #ifndef R48_STEP_TABLE_GLOBAL
 #define R48_STEP_TABLE_GLOBAL 0    // 1: step_kernel (reward_mode 0) reads the LR table from global memory, no staging
 #endif
+#ifndef R48_RING_L2_HINT
+#define R48_RING_L2_HINT 64          // ring_get: 64 = ld.global.L2::64B (half the DRAM bytes of the default, same time), 1 = also .nc.L1::no_allocate, 0 = plain
+#endif
 #ifndef R48_AFTER_PREFETCH
 #define R48_AFTER_PREFETCH 1
 #endif
@@ -627,8 +630,16 @@ __device__ __forceinline__ void ring_get(const RingRefs &r, uint64_t slot, uint6
                                          int32_t &reward, uint64_t &next_state, uint32_t &done)
 {
     uint64_t word2, unused;
+#if R48_RING_L2_HINT == 64
+    asm volatile("ld.global.L2::64B.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(state), "=l"(next_state), "=l"(word2), "=l"(unused) : "l"(r.slots + slot));
+#elif R48_RING_L2_HINT == 1
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(state), "=l"(next_state), "=l"(word2), "=l"(unused) : "l"(r.slots + slot));
+#else
     asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];"
                  : "=l"(state), "=l"(next_state), "=l"(word2), "=l"(unused) : "l"(r.slots + slot));
+#endif
     reward = (int32_t)(uint32_t)word2;
     action = (uint32_t)(word2 >> 32) & 0xFFu;
     done = (uint32_t)(word2 >> 40) & 0xFFu;

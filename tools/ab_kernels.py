@@ -24,6 +24,8 @@ VARIANTS = {
     "unroll_pf0": ["-DR48_STEP_UNROLL=1", "-DR48_STEP_GATE_EARLY=1", "-DR48_STEP_PREFETCH=0"],
     "unroll_pf2": ["-DR48_STEP_UNROLL=1", "-DR48_STEP_GATE_EARLY=1", "-DR48_STEP_PREFETCH=2"],
     "gate_early": ["-DR48_STEP_GATE_EARLY=1"],
+    "ring64": ["-DR48_RING_L2_HINT=64"],
+    "ringnc": ["-DR48_RING_L2_HINT=1"],
     "nopred": ["-DR48_PRED_TRANSPOSE=0"],                                # transposes behind a branch instead of predicated
     "glb": ["-DR48_STEP_TABLE_GLOBAL=1"],                                # step_kernel: LR table from global memory / L1, no staging
     "nopipe": ["-DR48_AFTER_PIPE=0"],
