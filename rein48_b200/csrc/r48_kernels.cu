@@ -44,6 +44,9 @@ namespace r48 {
 #ifndef R48_RING_L2_HINT
 #define R48_RING_L2_HINT 64          // ring_get: 64 = ld.global.L2::64B (half the DRAM bytes of the default, same time), 1 = also .nc.L1::no_allocate, 0 = plain
 #endif
+#ifndef R48_UNGUARDED_TICKS
+#define R48_UNGUARDED_TICKS 4000u    // rollout: ticks below this cannot hold a 16384 tile (0 = always take the guarded body: test builds)
+#endif
 #ifndef R48_AFTER_PREFETCH
 #define R48_AFTER_PREFETCH 1
 #endif
@@ -1110,7 +1113,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(RolloutParams p)
             }
         };
         // parked lanes (live == false) sit on the empty board
-        if (__all_sync(kFull, tick < 4000u || !live)) four_ticks(std::false_type{});
+        if (__all_sync(kFull, tick < R48_UNGUARDED_TICKS || !live)) four_ticks(std::false_type{});
         else four_ticks(std::true_type{});
       }
     }

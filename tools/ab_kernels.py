@@ -26,6 +26,7 @@ VARIANTS = {
     "gate_early": ["-DR48_STEP_GATE_EARLY=1"],
     "ring64": ["-DR48_RING_L2_HINT=64"],
     "ringnc": ["-DR48_RING_L2_HINT=1"],
+    "guarded": ["-DR48_UNGUARDED_TICKS=0u"],                             # rollout: always the range-guarded lookup body (must give the same outputs)
     "nopred": ["-DR48_PRED_TRANSPOSE=0"],                                # transposes behind a branch instead of predicated
     "glb": ["-DR48_STEP_TABLE_GLOBAL=1"],                                # step_kernel: LR table from global memory / L1, no staging
     "nopipe": ["-DR48_AFTER_PIPE=0"],
