@@ -724,3 +724,30 @@ def test_env_step_in_a_cuda_graph(r48, orc):
     assert (env.env_episodes.cpu().numpy().view(np.uint32) == eps).all()
     assert (env.done.cpu().numpy() == o_d).all()
     assert (env.obs.cpu().numpy() == orc.decode_batch(boards, "float32")).all()
+
+
+def test_integration_md_ctypes_stub_runs(r48, orc):
+    """The binding INTEGRATION.md section 3 tells a Rein48 maintainer to add is executed as written
+    (only the library path is substituted) and checked against the oracle."""
+    import os, re, types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# game/r48_binding\.py.*?)```", text, re.S).group(1)
+    block = block.replace('ctypes.CDLL("libr48.so")', 'ctypes.CDLL(%r)' % r48._native.LIB_PATH)
+    mod = types.ModuleType("r48_binding")
+    exec(compile(block, "INTEGRATION.md", "exec"), mod.__dict__)
+    assert mod.pack([[2, 0, 0, 0], [0, 4, 0, 0], [0, 0, 0, 0], [0, 0, 0, 2048]]) == orc.encode(
+        [[2, 0, 0, 0], [0, 4, 0, 0], [0, 0, 0, 0], [0, 0, 0, 2048]])
+    b = random_boards(5001, 91)
+    a = np.random.default_rng(5).integers(0, 4, b.size).astype(np.uint8)
+    out, reward, done = mod.step_batch(b, a, SEED, 7, board_base=11)
+    o_b, o_r, o_d = orc.step_batch(b, a, SEED, 11, 7)
+    assert (out == o_b).all() and (reward == o_r).all() and (done == o_d.astype(bool)).all()
+    fb, ln, st = mod.random_rollouts(3000, SEED, board_base=5)
+    o_fb, o_ln = orc.rollout(3000, SEED, 5)
+    assert (fb == o_fb).all() and (ln == o_ln).all() and int(st[0]) == 3000
+    scores, lengths = mod.random_scores(3000, SEED, board_base=5)
+    assert (scores == orc.scores(o_fb)).all() and (lengths == np.minimum(o_ln, 8191)).all()
+    a[17] = 9
+    with pytest.raises(ValueError):
+        mod.step_batch(b, a, SEED, 7)
