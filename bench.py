@@ -591,7 +591,7 @@ def run_ours(args):
     def e2e_leg(make_out, records, d2h_per_episode):
         out = make_out()
         r48.random_rollouts_host(n, seed=SEED + 2000, device=local_rank, board_base=base, out=out, records=records)
-        reps = max(1, min(args.steps, 3))
+        reps = max(1, min(args.steps, 10))
         barrier()
         t0 = time.perf_counter()
         steps_done = 0
