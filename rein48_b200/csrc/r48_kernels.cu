@@ -1477,7 +1477,10 @@ struct DeviceState {
     size_t arena_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // D2H of finished chunks overlaps the next chunk's kernel
+    cudaStream_t stream2 = nullptr;          // rollout chunks alternate between `stream` and this one (see r48_rollout_host_ex)
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    cudaEvent_t stats_done[2] = {nullptr, nullptr};
+    cudaEvent_t join = nullptr;
 };
 
 DeviceState g_dev[kMaxDevices];
@@ -1689,6 +1692,10 @@ int arena_reserve(DeviceState &d, size_t bytes)
         CK(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&d.chunk_done[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&d.chunk_done[1], cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&d.stats_done[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&d.stats_done[1], cudaEventDisableTiming));
     }
     if (d.arena_bytes >= bytes) return R48_OK;
     if (d.arena) CK(cudaFree(d.arena));
@@ -2277,20 +2284,27 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
     const size_t nb = (size_t)n;
     const size_t o_fb = 0, o_len = up256(nb * 8), o_rec = o_len + up256(nb * 4),
                  o_stats = o_rec + up256(records ? nb * 4 : 0), o_ws = o_stats + up256(R48_STATS_WORDS * 8),
-                 total = o_ws + R48_ROLLOUT_WORKSPACE_BYTES;
+                 total = o_ws + 2 * R48_ROLLOUT_WORKSPACE_BYTES;
     if ((rc = arena_reserve(*d, total))) return rc;
     uint64_t *d_fb = (uint64_t *)(d->arena + o_fb);
     uint32_t *d_len = (uint32_t *)(d->arena + o_len);
     uint32_t *d_rec = (uint32_t *)(d->arena + o_rec);
     uint64_t *d_stats = (uint64_t *)(d->arena + o_stats);
-    cudaStream_t s = d->stream, c = d->copy_stream;
-    if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, s));
+    cudaStream_t cs[2] = {d->stream, d->stream2}, c = d->copy_stream;
+    if (stats) CK(cudaMemsetAsync(d_stats, 0, R48_STATS_WORDS * 8, cs[0]));
+    CK(cudaEventRecord(d->join, cs[0]));
+    CK(cudaStreamWaitEvent(cs[1], d->join, 0));
     // Large batches go in chunks of 2^24 episodes: the per-episode results of chunk i travel to
     // the host on the copy stream while chunk i+1 is being played (67 MB of records per chunk: 1.2 ms
-    // of PCIe under 8 ms of play; every chunk costs ~0.1 ms in launch tails and gaps, so not smaller).
+    // of PCIe under 8 ms of play).
     // The copy of the LAST chunk is the only one left exposed, so the chunks shrink toward the end
     // (..., 2^24, 2^23, 2^22, 2^21, 2^20, 2^20): small chunks run a little less efficiently but hide
     // most of that tail.
+    // Chunks ALTERNATE between two streams: a rollout launch ends with ~0.1 ms in which its last long
+    // games keep a shrinking number of SMs busy; the next chunk's kernel, already queued on the other
+    // stream, takes every SM as it is vacated (a kernel behind it on the SAME stream would wait for
+    // the last CTA).  Each stream has its own episode-queue workspace; the statistics kernels add
+    // into one vector with atomics.
     const int64_t big = (int64_t)1 << 24, small = (int64_t)1 << 20;
     int slot = 0;
     for (int64_t off = 0, m = 0; off < n; off += m, slot ^= 1) {
@@ -2300,9 +2314,20 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
         else if (left > 2 * big) m = big;
         else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
         else m = left;
+        cudaStream_t s = cs[slot];
         rc = r48_rollout_policy(m, seed, board_base + (uint64_t)off, policy, d_fb + off, d_len + off, nullptr,
-                                d->arena + o_ws, s);
+                                d->arena + o_ws + (size_t)slot * R48_ROLLOUT_WORKSPACE_BYTES, s);
         if (rc) return rc;
+        // what the rollout kernel itself wrote can leave as soon as it has finished; the statistics
+        // pass of this chunk gets its SMs only when the NEXT chunk's kernel starts to drain
+        if (final_boards || lengths) {
+            CK(cudaEventRecord(d->chunk_done[slot], s));
+            CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
+            if (final_boards)
+                CK(cudaMemcpyAsync(final_boards + off, d_fb + off, (size_t)m * 8, cudaMemcpyDeviceToHost, c));
+            if (lengths)
+                CK(cudaMemcpyAsync(lengths + off, d_len + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+        }
         if (stats) {                                           // statistics and records in one pass over the chunk
             stats_kernel<<<grid_for(m, 256, d->sms, 8), 256, 0, s>>>(d_fb + off, d_len + off, m,
                                                                      (unsigned long long *)d_stats, records ? d_rec + off : nullptr);
@@ -2310,19 +2335,17 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
         } else if (records && (rc = r48_episode_records(d_fb + off, d_len + off, d_rec + off, m, s))) {
             return rc;
         }
-        if (final_boards || lengths || records) {
-            CK(cudaEventRecord(d->chunk_done[slot], s));
-            CK(cudaStreamWaitEvent(c, d->chunk_done[slot], 0));
-            if (final_boards)
-                CK(cudaMemcpyAsync(final_boards + off, d_fb + off, (size_t)m * 8, cudaMemcpyDeviceToHost, c));
-            if (lengths)
-                CK(cudaMemcpyAsync(lengths + off, d_len + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
-            if (records)
-                CK(cudaMemcpyAsync(records + off, d_rec + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+        if (records) {
+            CK(cudaEventRecord(d->stats_done[slot], s));
+            CK(cudaStreamWaitEvent(c, d->stats_done[slot], 0));
+            CK(cudaMemcpyAsync(records + off, d_rec + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
         }
     }
-    if (stats) CK(cudaMemcpyAsync(stats, d_stats, R48_STATS_WORDS * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(d->join, cs[1]));                       // the statistics are complete when both streams are
+    CK(cudaStreamWaitEvent(cs[0], d->join, 0));
+    if (stats) CK(cudaMemcpyAsync(stats, d_stats, R48_STATS_WORDS * 8, cudaMemcpyDeviceToHost, cs[0]));
+    CK(cudaStreamSynchronize(cs[0]));
+    CK(cudaStreamSynchronize(cs[1]));
     CK(cudaStreamSynchronize(c));
     return R48_OK;
 }
@@ -2344,6 +2367,9 @@ int r48_shutdown(void)
         if (d.arena) cudaFree(d.arena);
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
+        if (d.join) cudaEventDestroy(d.join);
+        for (int e = 0; e < 2; e++) if (d.stats_done[e]) cudaEventDestroy(d.stats_done[e]);
         for (int e = 0; e < 2; e++) if (d.chunk_done[e]) cudaEventDestroy(d.chunk_done[e]);
         if (d.left) cudaFree(d.left);
         if (d.merges) cudaFree(d.merges);
