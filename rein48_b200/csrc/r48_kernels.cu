@@ -1481,6 +1481,8 @@ struct DeviceState {
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
     cudaEvent_t stats_done[2] = {nullptr, nullptr};
     cudaEvent_t join = nullptr;
+    cudaEvent_t probe[4] = {nullptr, nullptr, nullptr, nullptr};   // around the first chunk's kernel and its copy
+    float copy_over_play = 0.0f;             // measured by the previous r48_rollout_host_ex call on this device
 };
 
 DeviceState g_dev[kMaxDevices];
@@ -1696,6 +1698,7 @@ int arena_reserve(DeviceState &d, size_t bytes)
         CK(cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&d.stats_done[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&d.stats_done[1], cudaEventDisableTiming));
+        for (int e = 0; e < 4; e++) CK(cudaEventCreate(&d.probe[e]));
     }
     if (d.arena_bytes >= bytes) return R48_OK;
     if (d.arena) CK(cudaFree(d.arena));
@@ -2297,27 +2300,36 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
     // Large batches go in chunks of 2^24 episodes: the per-episode results of chunk i travel to
     // the host on the copy stream while chunk i+1 is being played (67 MB of records per chunk: 1.2 ms
     // of PCIe under 8 ms of play).
-    // The copy of the LAST chunk is the only one left exposed, so the chunks shrink toward the end
-    // (..., 2^24, 2^23, 2^22, 2^21, 2^20, 2^20): small chunks run a little less efficiently but hide
-    // most of that tail.
+    // The copy of the LAST chunk is the only one left exposed, so the chunks shrink toward the end:
+    // each half of what is left (..., 2^24, 2^23, ..., 2^20, 2^20) when a chunk's copy takes less than
+    // 0.3 of its play -- one GPU on the host: 0.07 ns per record against 0.5 ns of play per
+    // episode -- and a quarter of what is left (16M, 12M, 9M, 7M, ...) when it does not: eight ranks
+    // sharing the host's memory bandwidth get ~11 GB/s each, 0.36 ns per record, and halved chunks
+    // pile their copies up at the end.  The ratio is the one the previous call measured on its first
+    // chunk (events around the kernel and around the copy); every extra chunk costs ~0.1 ms.
     // Chunks ALTERNATE between two streams: a rollout launch ends with ~0.1 ms in which its last long
     // games keep a shrinking number of SMs busy; the next chunk's kernel, already queued on the other
     // stream, takes every SM as it is vacated (a kernel behind it on the SAME stream would wait for
     // the last CTA).  Each stream has its own episode-queue workspace; the statistics kernels add
     // into one vector with atomics.
     const int64_t big = (int64_t)1 << 24, small = (int64_t)1 << 20;
+    const int64_t shrink = d->copy_over_play > 0.3f ? 4 : 2;
+    bool probed = false;
     int slot = 0;
     for (int64_t off = 0, m = 0; off < n; off += m, slot ^= 1) {
         const int64_t left = n - off;
         if (n <= ((int64_t)1 << 23) || !(final_boards || lengths || records))
             m = left;                                          // small batches, or nothing to copy per episode: one launch
-        else if (left > 2 * big) m = big;
-        else if (left > 2 * small) m = (left / 2 + small - 1) / small * small;   // halve, in 2^20 units
+        else if (left > shrink * big) m = big;
+        else if (left > 2 * small) m = (left / shrink + small - 1) / small * small;   // in 2^20 units
         else m = left;
         cudaStream_t s = cs[slot];
+        const bool probing = off == 0 && m < n && (final_boards || lengths || records);
+        if (probing) CK(cudaEventRecord(d->probe[0], s));
         rc = r48_rollout_policy(m, seed, board_base + (uint64_t)off, policy, d_fb + off, d_len + off, nullptr,
                                 d->arena + o_ws + (size_t)slot * R48_ROLLOUT_WORKSPACE_BYTES, s);
         if (rc) return rc;
+        if (probing) { CK(cudaEventRecord(d->probe[1], s)); CK(cudaStreamWaitEvent(c, d->probe[1], 0)); CK(cudaEventRecord(d->probe[2], c)); }
         // what the rollout kernel itself wrote can leave as soon as it has finished; the statistics
         // pass of this chunk gets its SMs only when the NEXT chunk's kernel starts to drain
         if (final_boards || lengths) {
@@ -2327,6 +2339,7 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
                 CK(cudaMemcpyAsync(final_boards + off, d_fb + off, (size_t)m * 8, cudaMemcpyDeviceToHost, c));
             if (lengths)
                 CK(cudaMemcpyAsync(lengths + off, d_len + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+            if (probing) CK(cudaEventRecord(d->probe[3], c));
         }
         if (stats) {                                           // statistics and records in one pass over the chunk
             stats_kernel<<<grid_for(m, 256, d->sms, 8), 256, 0, s>>>(d_fb + off, d_len + off, m,
@@ -2338,8 +2351,12 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
         if (records) {
             CK(cudaEventRecord(d->stats_done[slot], s));
             CK(cudaStreamWaitEvent(c, d->stats_done[slot], 0));
+            const bool probe_here = probing && !(final_boards || lengths);
+            if (probe_here) CK(cudaEventRecord(d->probe[2], c));      // the copy alone, not the wait before it
             CK(cudaMemcpyAsync(records + off, d_rec + off, (size_t)m * 4, cudaMemcpyDeviceToHost, c));
+            if (probe_here) CK(cudaEventRecord(d->probe[3], c));
         }
+        probed = probed || probing;
     }
     CK(cudaEventRecord(d->join, cs[1]));                       // the statistics are complete when both streams are
     CK(cudaStreamWaitEvent(cs[0], d->join, 0));
@@ -2347,6 +2364,12 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
     CK(cudaStreamSynchronize(cs[0]));
     CK(cudaStreamSynchronize(cs[1]));
     CK(cudaStreamSynchronize(c));
+    if (probed) {
+        float play_ms = 0.0f, copy_ms = 0.0f;
+        if (cudaEventElapsedTime(&play_ms, d->probe[0], d->probe[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&copy_ms, d->probe[2], d->probe[3]) == cudaSuccess && play_ms > 0.0f)
+            d->copy_over_play = copy_ms / play_ms;
+    }
     return R48_OK;
 }
 
@@ -2370,6 +2393,7 @@ int r48_shutdown(void)
         if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.join) cudaEventDestroy(d.join);
         for (int e = 0; e < 2; e++) if (d.stats_done[e]) cudaEventDestroy(d.stats_done[e]);
+        for (int e = 0; e < 4; e++) if (d.probe[e]) cudaEventDestroy(d.probe[e]);
         for (int e = 0; e < 2; e++) if (d.chunk_done[e]) cudaEventDestroy(d.chunk_done[e]);
         if (d.left) cudaFree(d.left);
         if (d.merges) cudaFree(d.merges);
