@@ -296,6 +296,9 @@ int r48_rollout_host(int64_t n, uint64_t seed, uint64_t board_base, uint64_t *fi
  * records[i] packs what main.py:48 prints per game and the episode length into one word:
  *     bits 31..13  score / 2   (score = np.sum(state_matrix); always even, at most 2^19: exact)
  *     bits 12..0   min(length, 8191) */
+/* (Large batches are played in chunks whose copies overlap the next chunk's kernel; the chunk sizes
+ * adapt to the copy / play time ratio the previous call measured on this device.  Results do not
+ * depend on the chunking: every draw is keyed by (seed, board id, tick).) */
 #define R48_RECORD_SCORE(r)  (((uint32_t)(r) >> 13) << 1)
 #define R48_RECORD_LENGTH(r) ((uint32_t)(r) & 8191u)
 int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int policy,
