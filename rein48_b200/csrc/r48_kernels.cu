@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <type_traits>
 #include <new>
@@ -2313,7 +2314,10 @@ int r48_rollout_host_ex(int64_t n, uint64_t seed, uint64_t board_base, int polic
     // the last CTA).  Each stream has its own episode-queue workspace; the statistics kernels add
     // into one vector with atomics.
     const int64_t big = (int64_t)1 << 24, small = (int64_t)1 << 20;
-    const int64_t shrink = d->copy_over_play > 0.3f ? 4 : 2;
+    int64_t shrink = d->copy_over_play > 0.3f ? 4 : 2;
+    if (const char *forced = getenv("R48_HOST_CHUNK_SHRINK")) {          // tests: take the other schedule
+        if (forced[0] == '2' || forced[0] == '4') shrink = forced[0] - '0';
+    }
     bool probed = false;
     int slot = 0;
     for (int64_t off = 0, m = 0; off < n; off += m, slot ^= 1) {

@@ -531,9 +531,12 @@ def test_rollout_host_records(r48, orc):
     assert (g.records.numpy().view(np.uint32) == orc.episode_records(gfb, gln)).all()
 
 
-def test_rollout_host_chunked(r48, orc):
-    """n > 2^24 goes in 2^23-episode chunks with the D2H copies overlapped: same episodes as one
-    device launch, and the tail chunk checked against the oracle."""
+@pytest.mark.parametrize("shrink", ["2", "4"])
+def test_rollout_host_chunked(r48, orc, monkeypatch, shrink):
+    """n > 2^23 goes in chunks (alternating between two streams, each half or a quarter of what is
+    left) with the D2H copies overlapped: same episodes as one device launch whatever the schedule,
+    and the tail checked against the oracle."""
+    monkeypatch.setenv("R48_HOST_CHUNK_SHRINK", shrink)
     n = (1 << 24) + 12345
     out = r48.random_rollouts_host(n, seed=9, board_base=5)
     dev_res = r48.random_rollouts(n, seed=9, board_base=5)
@@ -543,6 +546,12 @@ def test_rollout_host_chunked(r48, orc):
     fb, ln = orc.rollout(12345, 9, 5 + (1 << 24), threads=4)
     assert (out.final_boards.numpy().view(np.uint64)[1 << 24:] == fb).all()
     assert (out.lengths.numpy().view(np.uint32)[1 << 24:] == ln).all()
+    # the packed records of the same job (written by the statistics pass of each chunk)
+    rec = r48.random_rollouts_host(n, seed=9, board_base=5, records=True)
+    score, _ = r48.scores(dev_res.final_boards)
+    assert (r48.record_scores(rec.records).cuda() == score.to(torch.int64)).all()
+    assert (r48.record_lengths(rec.records).cuda() == dev_res.lengths.to(torch.int64).clamp(max=8191)).all()
+    assert (rec.stats.cuda() == dev_res.stats).all()
 
 
 @pytest.mark.parametrize("n", [70001, (1 << 19) + (1 << 18) + 3])      # single launch / chunked pipeline
