@@ -28,7 +28,7 @@
  *     merge two 32768 tiles.
  *   - Threads: the device entry points keep no per-call state and may be called from any number
  *     of host threads (each on its own stream).  The *_host entry points share one scratch
- *     arena, two streams and two events per device and take a per-device mutex for the whole
+ *     arena, their streams and events per device and take a per-device mutex for the whole
  *     call: concurrent calls on one device are safe and run one after another, calls on
  *     different devices run concurrently.  r48_last_error() is thread-local.
  *   - reward_mode 0 = reference (reward is always 0, GameClient.py:138);
