@@ -370,8 +370,8 @@ __device__ __forceinline__ void illegal_action(uint32_t &lo, uint32_t &hi, uint6
 
 // Work split: every CTA owns one contiguous slice of the batch (equal slices, so all SMs finish
 // together even when a launch is only a few trips long -- 2^20 boards are 7 boards per thread);
-// a thread takes one unit per trip and the unit of its NEXT trip is prefetched into L2 while it
-// computes, so that the next loads find their data there instead of waiting on HBM.  VEC: a unit
+// a thread takes one unit per trip and loads the unit of its NEXT trip into registers before it
+// computes the current one, so that the loads have a whole trip to land.  VEC: a unit
 // is a PAIR of boards moved with 128-bit loads/stores (needs 16-byte aligned in/out, 8-byte
 // reward, 2-byte action/done); otherwise a unit is one board.  The loop is deliberately bare: the
 // kernel runs at the SM's integer issue ceiling, so every bookkeeping instruction per trip is a
