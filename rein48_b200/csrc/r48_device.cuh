@@ -5,16 +5,19 @@
 // here is integer-pipe work; there is no tensor-core or floating-point math on this path.
 //
 // Reference behaviour restated by these functions (file:line in nevertiree/Rein48):
-//   move_*          Game.update_matrix           game/GameClient.py:129-254
-//   spawn_*         Game.random_fill_grid        game/GameClient.py:102-127
-//   is_stuck/...    Game.has_game_over           game/GameClient.py:65-94
-//   philox draws    random.randint/uniform       control/rand.py:11, GameClient.py:121,125
+//   rows_lr / rows_l16 / move_all / transpose   Game.update_matrix      game/GameClient.py:129-254
+//   count_blanks / kth_blank / spawn_tile       Game.random_fill_grid   game/GameClient.py:102-127
+//   game_over / no_equal_neighbours             Game.has_game_over      game/GameClient.py:65-94
+//   philox4x32 / draw_word                      random.randint/uniform  control/rand.py:11, GameClient.py:121,125
 #pragma once
 #include <stdint.h>
 
 // Build-time switches (A/B-timed on a B200, see DESIGN.md "measured and rejected"):
 //   R48_FMA_INDEX  table addresses by IMAD.WIDE / IMAD.HI (FMA pipe) instead of SHF + LOP3 (ALU pipe)
 //   R48_SWIZZLE    XOR bits 7..11 of the row into the bank bits of its table slot
+//   R48_PRED_TRANSPOSE (default 1)  conditional transposes without a branch (transpose_where)
+// and in r48_kernels.cu: R48_STEP_UNROLL / _PREFETCH / _GATE_EARLY / _TABLE_GLOBAL, R48_AFTER_PIPE /
+// _PREFETCH, R48_CALLS_PER_ITER, R48_UNGUARDED_TICKS, R48_RING_L2_HINT.
 #ifndef R48_FMA_INDEX
 #define R48_FMA_INDEX 0
 #endif

@@ -13,6 +13,7 @@
 //                         <policy, record>: random | greedy-blanks; play | replay-and-record
 //   stats/scores/records/decode/encode  readout             main.py:48, a3c.py:195,205
 //   ring_append/ring_sample  Replay.store / Replay.sample   algorithm/ddpg/replay.py:8-47
+//   game_view_kernel      Game.step for a host-side player main.py:36-42 over GameClient.py:40-51
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
