@@ -198,3 +198,15 @@ def test_two_rank_gloo_allreduce_is_exact(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_integration_md_stub_is_valid_python_and_binds_declared_symbols():
+    """The ctypes stub in INTEGRATION.md compiles, and every r48_* name it uses is declared in r48.h
+    (the GPU suite executes it against the library)."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# game/r48_binding\.py.*?)```", text, re.S).group(1)
+    compile(block, "INTEGRATION.md", "exec")
+    header = open(os.path.join(ROOT, "include", "r48.h")).read()
+    used = set(re.findall(r"_lib\.(r48_\w+)", block))
+    assert used and all(re.search(r"\b%s\s*\(" % name, header) for name in used), used
